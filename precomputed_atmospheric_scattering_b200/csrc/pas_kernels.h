@@ -1,0 +1,76 @@
+// Launch wrappers of the sm_100a kernels (one per pass of atmosphere/model.cc:1048-1215).
+// All tables are planar fp32 in HBM: tab[c][k][j][x] with x fastest (x = i_nu * mu_s_n + i_mu_s for
+// the 4-D tables), i.e. the reference's texel order with one plane per spectral channel. Every
+// launcher enqueues on `stream` and returns the CUDA status of the launch.
+#ifndef PAS_B200_CSRC_PAS_KERNELS_H_
+#define PAS_B200_CSRC_PAS_KERNELS_H_
+
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+
+#include "pas_types.h"
+
+namespace pas {
+
+// Output of the passes that also feed the final (possibly luminance-converted) tables.
+struct FinalTables {
+  void* scattering;        // RGBA interleaved [k][j][x][4], fp32 or fp16
+  void* single_mie;        // RGBA interleaved or nullptr (combined textures)
+  float* irradiance;       // RGBA interleaved fp32 [j][i][4]
+  int half_precision;      // scattering / single_mie stored as __half
+  int accumulate;          // 0: first channel group overwrites, 1: adds (GL blend, model.cc:1083)
+};
+
+// T[c][j][i] = transmittance to the top boundary (ComputeTransmittanceToTopAtmosphereBoundaryTexture,
+// functions.glsl:454-463). One warp per texel, 501 samples split across lanes, fp64.
+cudaError_t launch_transmittance(const PasGeometry& g, const PasSpectrum& s, float* T,
+                                 cudaStream_t stream);
+// Interleaves a 3-channel planar transmittance table into the RGBA32F product table.
+cudaError_t launch_pack_rgba(const float* planar, int n_texels, int nc, float* rgba,
+                             cudaStream_t stream);
+
+// dE[c][j][i] = direct irradiance (functions.glsl:1558-1567); zero-initialises the final E when
+// !accumulate (model.cc:139).
+cudaError_t launch_direct_irradiance(const PasGeometry& g, const PasSpectrum& s, const float* T,
+                                     float* dE, FinalTables fin, cudaStream_t stream);
+
+// Per-(layer, direction) constants of the density pass + ground factor
+// G[k][l][c] = T(r_k -> ground along theta_l)[c] * albedo[c] / pi (functions.glsl:1198-1213,1239-1240)
+// + per-layer scattering coefficients cR[k][c] = beta_R[c] rho_R(h_k), cM[k][c] = beta_M[c] rho_M(h_k).
+cudaError_t launch_density_setup(const PasGeometry& g, const PasSpectrum& s, const float* T,
+                                 PasDensityDir* dirs, float* G, float* cR, float* cM,
+                                 cudaStream_t stream);
+
+// Single scattering (functions.glsl:933-945) for layers [k_begin, k_end) + fused epilogue
+// S.rgb (+)= L.dR, S.a (+)= (L.dM).r, M (+)= L.dM (model.cc:142-157).
+cudaError_t launch_single_scattering(const PasGeometry& g, const PasSpectrum& s, const float* T,
+                                     float* dR, float* dM, FinalTables fin, int k_begin, int k_end,
+                                     cudaStream_t stream);
+
+// Scattering density of `order` >= 2 (functions.glsl:1348-1367) for layers [k_begin, k_end).
+// Reads dR, dM (order 2) or dS (order >= 3) and row 0 of dE.
+cudaError_t launch_scattering_density(const PasGeometry& g, const PasSpectrum& s,
+                                      const PasDensityDir* dirs, const float* G, const float* cR,
+                                      const float* cM, const float* dR, const float* dM,
+                                      const float* dS, const float* dE, int order, float* dJ,
+                                      int k_begin, int k_end, cudaStream_t stream);
+
+// Indirect irradiance from radiance of `order` (1: dR/dM with phase functions, else dS)
+// (functions.glsl:1573-1586) for rows [j_begin, j_end) + fused E += L.dE (model.cc:176-190).
+cudaError_t launch_indirect_irradiance(const PasGeometry& g, const PasSpectrum& s, const float* dR,
+                                       const float* dM, const float* dS, int order, float* dE,
+                                       FinalTables fin, int j_begin, int j_end,
+                                       cudaStream_t stream);
+
+// Multiple scattering (functions.glsl:1369-1383) for layers [k_begin, k_end) + fused
+// S.rgb += L.dS / RayleighPhaseFunction(nu) (model.cc:192-208).
+cudaError_t launch_multiple_scattering(const PasGeometry& g, const PasSpectrum& s, const float* T,
+                                       const float* dJ, float* dS, FinalTables fin, int k_begin,
+                                       int k_end, cudaStream_t stream);
+
+// Channel-group sizes the templated kernels are instantiated for.
+bool channel_count_supported(int nc);
+
+}  // namespace pas
+
+#endif  // PAS_B200_CSRC_PAS_KERNELS_H_
