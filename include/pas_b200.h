@@ -1,0 +1,205 @@
+/* pas_b200 -- C ABI of the B200-native LUT precomputation for
+ * ebruneton/precomputed_atmospheric_scattering.
+ *
+ * This is the drop-in boundary for ONE path of the reference: atmosphere::Model's constructor +
+ * Model::Init (atmosphere/model.cc:613-795, 866-975, 1048-1215), which fill the transmittance,
+ * scattering (+ optional single Mie) and irradiance tables. Every entry point names the reference
+ * interface it replaces. Plain C types only: pointers, sizes, doubles. All functions return a
+ * pas_status (0 = PAS_OK); pas_last_error() returns a human-readable message for the calling
+ * thread's last failure. Nothing here ever falls back to a CPU implementation: without a CUDA
+ * device pas_model_create fails with PAS_ERR_CUDA.
+ *
+ * Threading: calls on different pas_model handles are independent; one handle must not be used
+ * from two threads at once (the reference is single-threaded on its GL context,
+ * atmosphere/model.cc:866-975).
+ */
+#ifndef PAS_B200_H_
+#define PAS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PAS_B200_ABI_VERSION 1
+
+typedef enum pas_status {
+  PAS_OK = 0,
+  PAS_ERR_INVALID_ARGUMENT = 1,  /* bad sizes / unsorted wavelengths / top <= bottom / > 2 layers */
+  PAS_ERR_CUDA = 2,              /* CUDA runtime failure (message has the CUDA error string) */
+  PAS_ERR_NCCL = 3,              /* NCCL failure on the multi-GPU path */
+  PAS_ERR_UNSUPPORTED = 4,       /* table sizes outside what the kernels support */
+  PAS_ERR_STATE = 5,             /* e.g. reading a table before pas_model_init */
+  PAS_ERR_IO = 6                 /* file / shader-source I/O */
+} pas_status;
+
+/* atmosphere::DensityProfileLayer (atmosphere/model.h:165-178), SI units. */
+typedef struct pas_density_layer {
+  double width, exp_term, exp_scale, linear_term, constant_term;
+} pas_density_layer;
+
+/* Table sizes. The reference fixes them at compile time (atmosphere/constants.h:47-61); here they
+ * are run-time. Any field left 0 takes the reference's value
+ * (256x64, R=32, MU=128, MU_S=32, NU=8, 64x16). */
+typedef struct pas_lut_sizes {
+  int transmittance_width, transmittance_height;
+  int scattering_r, scattering_mu, scattering_mu_s, scattering_nu;
+  int irradiance_width, irradiance_height;
+} pas_lut_sizes;
+
+/* The 19 arguments of atmosphere::Model::Model (atmosphere/model.h:182-281), same meaning, same
+ * units (nm, W/m^2/nm, rad, m, m^-1), same rules: spectra are sampled at `wavelengths` and
+ * interpolated linearly, clamped at the ends (atmosphere/model.cc:535-552); density profiles have
+ * at most 2 layers, missing ones are zero layers below (atmosphere/model.cc:653-666). */
+typedef struct pas_model_params {
+  size_t num_wavelengths;
+  const double* wavelengths;
+  const double* solar_irradiance;
+  double sun_angular_radius;
+  double bottom_radius;
+  double top_radius;
+  size_t num_rayleigh_layers;
+  const pas_density_layer* rayleigh_density;
+  const double* rayleigh_scattering;
+  size_t num_mie_layers;
+  const pas_density_layer* mie_density;
+  const double* mie_scattering;
+  const double* mie_extinction;
+  double mie_phase_function_g;
+  size_t num_absorption_layers;
+  const pas_density_layer* absorption_density;
+  const double* absorption_extinction;
+  const double* ground_albedo;
+  double max_sun_zenith_angle;
+  double length_unit_in_meters;
+  unsigned int num_precomputed_wavelengths;
+  int combine_scattering_textures;
+  int half_precision;
+  /* ---- extensions (zero-initialise for reference behaviour) ---- */
+  pas_lut_sizes sizes;
+  int device;  /* CUDA device ordinal + 1; 0 = the calling thread's current device */
+} pas_model_params;
+
+typedef struct pas_model pas_model;
+
+/* The tables a Model owns (atmosphere/model.h:331-334). */
+typedef enum pas_texture {
+  PAS_TEXTURE_TRANSMITTANCE = 0,    /* RGBA32F, width x height                        */
+  PAS_TEXTURE_SCATTERING = 1,       /* RGBA16F/32F, (NU*MU_S) x MU x R                 */
+  PAS_TEXTURE_IRRADIANCE = 2,       /* RGBA32F, width x height                        */
+  PAS_TEXTURE_SINGLE_MIE = 3        /* RGBA16F/32F; absent with combined textures      */
+} pas_texture;
+
+typedef struct pas_texture_info {
+  int width, height, depth;   /* depth 1 for 2-D tables */
+  int channels;               /* always 4: texels are RGBA interleaved, x fastest, then y, z --
+                                 what glGetTexImage(GL_RGBA, ...) returns
+                                 (atmosphere/demo/webgl/precompute.cc:63-73) */
+  int bytes_per_channel;      /* 4 (float) or 2 (IEEE half) as stored on the device */
+  int present;                /* 0 if this model has no such table */
+} pas_texture_info;
+
+/* Replaces atmosphere::Model::Model (atmosphere/model.cc:613-795): validates and converts the
+ * parameters, allocates the tables in HBM. Does not precompute. */
+pas_status pas_model_create(const pas_model_params* params, pas_model** out_model);
+
+/* Replaces atmosphere::Model::~Model (atmosphere/model.cc:801-811). NULL is allowed. */
+void pas_model_destroy(pas_model* model);
+
+/* Replaces atmosphere::Model::Init(num_scattering_orders) (atmosphere/model.cc:866-975 and
+ * Precompute, :1048-1215): runs every pass on the GPU and returns when the tables are complete in
+ * device memory. May be called again (e.g. with another order count). */
+pas_status pas_model_init(pas_model* model, unsigned int num_scattering_orders);
+
+pas_status pas_model_texture_info(const pas_model* model, pas_texture which,
+                                  pas_texture_info* info);
+
+/* Device pointer of a table, for zero-copy consumers (CUDA-GL interop upload in the Model shim's
+ * SetProgramUniforms, atmosphere/model.cc:984-1011). Valid until the next init/destroy. */
+pas_status pas_model_texture_device_ptr(const pas_model* model, pas_texture which,
+                                        const void** device_ptr);
+
+/* Copies a table to host memory as RGBA float32 (as_float32 != 0: what
+ * glGetTexImage(GL_RGBA, GL_FLOAT) returns, the layout of the reference's .dat files,
+ * atmosphere/demo/webgl/precompute.cc:63-73) or in its stored precision. dst_bytes must match. */
+pas_status pas_model_read_texture(pas_model* model, pas_texture which, int as_float32, void* dst,
+                                  size_t dst_bytes);
+
+/* Writes transmittance.dat / scattering.dat / irradiance.dat (+ single_mie_scattering.dat) into
+ * `directory`, raw little-endian RGBA32F (atmosphere/demo/webgl/precompute.cc:85-106). */
+pas_status pas_model_save_dat(pas_model* model, const char* directory);
+
+/* The GLSL source atmosphere::Model::shader() compiles (atmosphere/model.cc:691-744, 769-772):
+ * header with the ATMOSPHERE constant + definitions.glsl + functions.glsl + the API wrappers.
+ * definitions.glsl / functions.glsl are read from `glsl_directory` (the reference checkout's
+ * atmosphere/ directory); they are inputs, not part of this library. Call with buffer == NULL to
+ * get the required size (including the terminating NUL) in *size. */
+pas_status pas_model_shader_source(const pas_model* model, const char* glsl_directory,
+                                   char* buffer, size_t* size);
+
+/* The SKY/SUN_SPECTRAL_RADIANCE_TO_LUMINANCE constants baked into that shader
+ * (atmosphere/model.cc:562-595, 668-686). out6 = sky rgb, sun rgb. */
+pas_status pas_model_luminance_factors(const pas_model* model, double* out6);
+
+/* Replaces the static atmosphere::Model::ConvertSpectrumToLinearSrgb
+ * (atmosphere/model.cc:1020-1040). */
+pas_status pas_convert_spectrum_to_linear_srgb(size_t n, const double* wavelengths,
+                                               const double* spectrum, double* r, double* g,
+                                               double* b);
+
+/* ---- introspection used by the parity tests and the bench (no reference counterpart) -------- */
+
+/* Number of spectral channels the model precomputes and their wavelengths
+ * (atmosphere/model.cc:907-924). Pass lambdas == NULL to query the count only. */
+pas_status pas_model_channels(const pas_model* model, int* num_channels, double* lambdas);
+
+/* luminance_from_radiance of all channels side by side, row-major [3][num_channels]
+ * (atmosphere/model.cc:909, 925-943). */
+pas_status pas_model_luminance_matrix(const pas_model* model, float* out);
+
+/* When enabled, Init keeps a device copy of every intermediate (planar per channel, texel order
+ * x fastest): "transmittance", "delta_irradiance_<n>", "delta_rayleigh", "delta_mie",
+ * "delta_density_<n>", "delta_multiple_<n>". Costs memory and time; off by default. */
+pas_status pas_model_set_capture(pas_model* model, int enabled);
+/* num_floats: in = capacity of dst, out = floats needed/copied. dst may be NULL to query. */
+pas_status pas_model_read_intermediate(pas_model* model, const char* name, float* dst,
+                                       size_t* num_floats);
+
+/* Teacher-forced single passes: upload planar per-channel inputs (same names as above, plus
+ * "delta_irradiance" / "delta_density" / "delta_multiple" for the live buffers) and run one phase
+ * of atmosphere/model.cc:1048-1215. phase: 0 transmittance, 1 direct irradiance, 2 single
+ * scattering, 3 scattering density(order), 4 indirect irradiance(order = order of the radiance
+ * integrated), 5 multiple scattering. Results are read back with pas_model_read_intermediate
+ * using the live-buffer names. */
+pas_status pas_model_write_intermediate(pas_model* model, const char* name, const float* src,
+                                        size_t num_floats);
+pas_status pas_model_run_phase(pas_model* model, int phase, int order);
+
+/* Device time of the last pas_model_init, per phase (CUDA events on the model's stream), in ms.
+ * names/ms are filled up to *count entries; *count returns the number available. */
+pas_status pas_model_last_timings(const pas_model* model, int* count, const char** names,
+                                  float* ms);
+/* Kernels launched by the last pas_model_init. */
+pas_status pas_model_last_launch_count(const pas_model* model, int* launches);
+
+/* ---- multi-GPU (one process per GPU; no reference counterpart) ------------------------------ */
+
+#define PAS_NCCL_UNIQUE_ID_BYTES 128
+/* Fills a 128-byte NCCL unique id (call on rank 0, broadcast it with any host-side transport). */
+pas_status pas_nccl_unique_id(void* id_bytes);
+/* Attaches the model to a world of `world_size` processes: scattering layers are split into
+ * contiguous r-slabs, one per rank; the scattering-density table is all-gathered over NVLink and
+ * the irradiance partial sums all-reduced between orders. Must be called by every rank before
+ * pas_model_init. After Init every rank holds the complete final tables. */
+pas_status pas_model_attach_world(pas_model* model, int rank, int world_size,
+                                  const void* nccl_unique_id_bytes);
+
+const char* pas_last_error(void);
+int pas_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* PAS_B200_H_ */

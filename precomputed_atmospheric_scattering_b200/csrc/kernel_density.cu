@@ -166,12 +166,14 @@ density_kernel(const __grid_constant__ PasGeometry g, const PasDensityDir* __res
     const double gb = (double)d.dg_over_b * half;
     dc.g_a = (float)ga;
     dc.g_b = (float)gb;
+    // knots [i0, i1] cover every x the azimuth loop can produce (nu1 in [-1, 1]); x outside
+    // [0, e_w - 1] is clamped by the saturating ramps exactly like the fetch's index clamp
     int i0 = (int)floor(ga - gb - 1e-3);
-    i0 = i0 < 0 ? 0 : (i0 > e_w - 1 ? e_w - 1 : i0);
+    i0 = i0 < 0 ? 0 : (i0 > e_w - 2 ? e_w - 2 : i0);
     int i1 = (int)ceil(ga + gb + 1e-3);
-    i1 = i1 > e_w - 1 ? e_w - 1 : i1;
+    i1 = i1 > e_w - 1 ? e_w - 1 : (i1 < i0 + 1 ? i0 + 1 : i1);
     dc.win_i0 = i0;
-    dc.win_n = d.hit ? (i1 - i0 > 0 ? i1 - i0 : 0) : 0;
+    dc.win_n = d.hit ? i1 - i0 : 0;
     dc.pad = 0;
     sDir[tid] = dc;
   }
@@ -340,9 +342,9 @@ density_kernel(const __grid_constant__ PasGeometry g, const PasDensityDir* __res
         float eR = 0.f, eM = 0.f;
 #pragma unroll
         for (int t = 0; t < kNG; ++t) {
-          // ramps past the last knot have zero differences (padding), so over-reading is exact
-          eR = fmaf(de[t < e_pad ? t : 0], W.gramp[0][t], eR);
-          eM = fmaf(de[t < e_pad ? t : 0], W.gramp[1][t], eM);
+          // ramps past the last knot read the zero padding of sDE
+          eR = fmaf(de[t], W.gramp[0][t], eR);
+          eM = fmaf(de[t], W.gramp[1][t], eM);
         }
         acc[c] = fmaf(sCR[c] * sG[l][c], eR, fmaf(sCM[c] * sG[l][c], eM, acc[c]));
       }

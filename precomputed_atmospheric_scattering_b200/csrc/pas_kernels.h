@@ -56,11 +56,13 @@ cudaError_t launch_scattering_density(const PasGeometry& g, const PasSpectrum& s
                                       int k_begin, int k_end, cudaStream_t stream);
 
 // Indirect irradiance from radiance of `order` (1: dR/dM with phase functions, else dS)
-// (functions.glsl:1573-1586) for rows [j_begin, j_end) + fused E += L.dE (model.cc:176-190).
+// (functions.glsl:1573-1586) for rows [j_begin, j_end) + fused E += L.dE (model.cc:176-190)
+// when fin.irradiance != nullptr. Only source layers [k_begin, k_end) contribute (the r-slab
+// owned by this rank; the partial sums are all-reduced by the caller).
 cudaError_t launch_indirect_irradiance(const PasGeometry& g, const PasSpectrum& s, const float* dR,
                                        const float* dM, const float* dS, int order, float* dE,
-                                       FinalTables fin, int j_begin, int j_end,
-                                       cudaStream_t stream);
+                                       FinalTables fin, int j_begin, int j_end, int k_begin,
+                                       int k_end, cudaStream_t stream);
 
 // Multiple scattering (functions.glsl:1369-1383) for layers [k_begin, k_end) + fused
 // S.rgb += L.dS / RayleighPhaseFunction(nu) (model.cc:192-208).

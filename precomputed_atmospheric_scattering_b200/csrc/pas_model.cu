@@ -1,0 +1,1067 @@
+// Host side of the C ABI (include/pas_b200.h): parameter conversion that mirrors
+// atmosphere::Model::Model (atmosphere/model.cc:613-795), the pass schedule that mirrors
+// Model::Init / Model::Precompute (atmosphere/model.cc:866-975, 1048-1215) with CUDA kernels in
+// place of the GL draws, table readback, and the r-slab multi-GPU exchange over NCCL.
+//
+// There is no CPU implementation of any pass in this library: every table is produced by the
+// kernels in kernels_setup.cu, kernel_raymarch.cu, kernel_density.cu and kernel_irradiance.cu.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <map>
+#include <memory>
+#include <sstream>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../../include/pas_b200.h"
+#include "cie1931.h"
+#include "pas_kernels.h"
+#include "pas_physics.cuh"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+pas_status fail(pas_status code, const std::string& msg) {
+  g_last_error = msg;
+  return code;
+}
+
+#define PAS_CUDA(expr)                                                                      \
+  do {                                                                                      \
+    cudaError_t e__ = (expr);                                                               \
+    if (e__ != cudaSuccess) {                                                               \
+      return fail(PAS_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));       \
+    }                                                                                       \
+  } while (0)
+
+// ---- NCCL, bound lazily so that the single-GPU path has no NCCL dependency -------------------
+struct NcclApi {
+  void* lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t,
+                            cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  bool ok = false;
+};
+NcclApi& nccl() {
+  static NcclApi api;
+  if (api.lib != nullptr || api.ok) return api;
+  api.lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (api.lib == nullptr) return api;
+#define PAS_SYM(field, name) *reinterpret_cast<void**>(&api.field) = dlsym(api.lib, name)
+  PAS_SYM(GetUniqueId, "ncclGetUniqueId");
+  PAS_SYM(CommInitRank, "ncclCommInitRank");
+  PAS_SYM(CommDestroy, "ncclCommDestroy");
+  PAS_SYM(AllGather, "ncclAllGather");
+  PAS_SYM(AllReduce, "ncclAllReduce");
+  PAS_SYM(GroupStart, "ncclGroupStart");
+  PAS_SYM(GroupEnd, "ncclGroupEnd");
+  PAS_SYM(GetErrorString, "ncclGetErrorString");
+#undef PAS_SYM
+  api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllGather &&
+           api.AllReduce && api.GroupStart && api.GroupEnd && api.GetErrorString;
+  return api;
+}
+#define PAS_NCCL(expr)                                                                      \
+  do {                                                                                      \
+    ncclResult_t r__ = (expr);                                                              \
+    if (r__ != ncclSuccess) {                                                               \
+      return fail(PAS_ERR_NCCL, std::string(#expr) + ": " + nccl().GetErrorString(r__));    \
+    }                                                                                       \
+  } while (0)
+
+// ---- spectra helpers (atmosphere/model.cc:521-595) -------------------------------------------
+// CieColorMatchingFunctionTableValue (model.cc:521-533): linear in the 5 nm table, 0 outside.
+double cie_value(double wavelength, int column) {
+  if (wavelength <= pas::kCieLambdaMin || wavelength >= pas::kCieLambdaMax) return 0.0;
+  double u = (wavelength - pas::kCieLambdaMin) / pas::kCieStep;
+  int row = static_cast<int>(std::floor(u));
+  u -= row;
+  const double* t = column == 1 ? pas::kCieXBar : (column == 2 ? pas::kCieYBar : pas::kCieZBar);
+  return t[row] * (1.0 - u) + t[row + 1] * u;
+}
+
+// Interpolate (model.cc:535-552): piecewise linear, clamped at both ends.
+double interpolate(const std::vector<double>& wl, const std::vector<double>& v, double wavelength) {
+  if (wavelength < wl[0]) return v[0];
+  for (size_t i = 0; i + 1 < wl.size(); ++i) {
+    if (wavelength < wl[i + 1]) {
+      double u = (wavelength - wl[i]) / (wl[i + 1] - wl[i]);
+      return v[i] * (1.0 - u) + v[i + 1] * u;
+    }
+  }
+  return v.back();
+}
+
+// ComputeSpectralRadianceToLuminanceFactors (model.cc:562-595), lumen.nm/watt.
+void luminance_factors(const std::vector<double>& wl, const std::vector<double>& solar,
+                       double lambda_power, double* k) {
+  k[0] = k[1] = k[2] = 0.0;
+  const double lam_rgb[3] = {680.0, 550.0, 440.0};
+  double solar_rgb[3];
+  for (int a = 0; a < 3; ++a) solar_rgb[a] = interpolate(wl, solar, lam_rgb[a]);
+  for (int lambda = 360; lambda < 830; ++lambda) {
+    const double xyz[3] = {cie_value(lambda, 1), cie_value(lambda, 2), cie_value(lambda, 3)};
+    const double irradiance = interpolate(wl, solar, lambda);
+    for (int a = 0; a < 3; ++a) {
+      double bar = pas::kXyzToSrgb[a][0] * xyz[0] + pas::kXyzToSrgb[a][1] * xyz[1] +
+                   pas::kXyzToSrgb[a][2] * xyz[2];
+      k[a] += bar * irradiance / solar_rgb[a] * std::pow(lambda / lam_rgb[a], lambda_power);
+    }
+  }
+  for (int a = 0; a < 3; ++a) k[a] *= pas::kMaxLuminousEfficacy;
+}
+
+struct DeviceBuffer {
+  void* p = nullptr;
+  size_t bytes = 0;
+  ~DeviceBuffer() { if (p) cudaFree(p); }
+  cudaError_t ensure(size_t n) {
+    if (n <= bytes) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+    cudaError_t e = cudaMalloc(&p, n);
+    if (e == cudaSuccess) bytes = n;
+    return e;
+  }
+  float* f() const { return static_cast<float*>(p); }
+};
+
+}  // namespace
+
+struct pas_model {
+  // ---- what the constructor was given (SI units) ----
+  std::vector<double> wavelengths, solar, rayleigh, mie_sca, mie_ext, absorption, albedo;
+  std::vector<pas_density_layer> profile_layers[3];
+  double sun_angular_radius = 0, bottom = 0, top = 0, mie_g = 0, max_sun_zenith = 0, unit = 1;
+  unsigned num_precomputed_wavelengths = 3;
+  bool combined = true, half = false;
+  // ---- derived ----
+  PasGeometry geom{};
+  std::vector<double> lambdas;      // channel wavelengths (model.cc:907-924)
+  std::vector<float> lum;           // [3][C] luminance_from_radiance (model.cc:909, 925-943)
+  std::vector<PasSpectrum> groups;  // channel groups, <= PAS_MAX_CH each
+  std::vector<int> group_offset;
+  PasSpectrum rgb_spectrum{};       // 680/550/440 nm, for the final transmittance (model.cc:951-963)
+  double sky_k[3] = {0, 0, 0}, sun_k[3] = {0, 0, 0};
+  // ---- device state ----
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  DeviceBuffer T, dE, dR, dM, dJ, dS, dirs, G, cR, cM, T_rgb, scratch;
+  DeviceBuffer S, M, E, T_rgba;
+  bool initialised = false;
+  bool capture = false;
+  std::map<std::string, std::unique_ptr<DeviceBuffer>> captured;
+  std::vector<std::pair<std::string, float>> timings;
+  int launches = 0;
+  // ---- multi-GPU ----
+  int rank = 0, world = 1;
+  ncclComm_t comm = nullptr;
+
+  size_t n_t() const { return (size_t)geom.sz.t_w * geom.sz.t_h; }
+  size_t n_e() const { return (size_t)geom.sz.e_w * geom.sz.e_h; }
+  size_t n_s() const { return (size_t)geom.sz.nu_n * geom.sz.mu_s_n * geom.sz.mu_n * geom.sz.r_n; }
+  size_t layer_texels() const { return (size_t)geom.sz.nu_n * geom.sz.mu_s_n * geom.sz.mu_n; }
+  int total_channels() const { return (int)lambdas.size(); }
+  size_t s_texel_bytes() const { return half ? 8 : 16; }
+  void slab(int* k_begin, int* k_end) const {
+    // contiguous r-slabs; the first (r_n % world) ranks get one extra layer
+    const int base = geom.sz.r_n / world, extra = geom.sz.r_n % world;
+    *k_begin = rank * base + std::min(rank, extra);
+    *k_end = *k_begin + base + (rank < extra ? 1 : 0);
+  }
+};
+
+namespace {
+
+PasSpectrum make_spectrum(const pas_model& m, const double* lambdas, int n, const float* lum3xC,
+                          int lum_stride, int lum_offset) {
+  PasSpectrum s{};
+  s.nc = n;
+  const double u = m.unit;
+  for (int c = 0; c < n; ++c) {
+    const double l = lambdas[c];
+    // scales as in the GLSL header (model.cc:718-734): coefficients are per length unit
+    s.solar[c] = interpolate(m.wavelengths, m.solar, l);
+    s.beta_r[c] = interpolate(m.wavelengths, m.rayleigh, l) * u;
+    s.beta_m_sca[c] = interpolate(m.wavelengths, m.mie_sca, l) * u;
+    s.beta_m_ext[c] = interpolate(m.wavelengths, m.mie_ext, l) * u;
+    s.beta_abs[c] = interpolate(m.wavelengths, m.absorption, l) * u;
+    s.albedo[c] = interpolate(m.wavelengths, m.albedo, l);
+    for (int a = 0; a < 3; ++a) {
+      s.lum[a][c] = lum3xC ? lum3xC[a * lum_stride + lum_offset + c] : (a == c ? 1.f : 0.f);
+    }
+  }
+  return s;
+}
+
+pas_status validate(const pas_model_params* p) {
+  if (p == nullptr) return fail(PAS_ERR_INVALID_ARGUMENT, "params is NULL");
+  if (p->num_wavelengths < 1 || !p->wavelengths || !p->solar_irradiance || !p->rayleigh_scattering ||
+      !p->mie_scattering || !p->mie_extinction || !p->absorption_extinction || !p->ground_albedo) {
+    return fail(PAS_ERR_INVALID_ARGUMENT, "missing spectrum arrays");
+  }
+  for (size_t i = 0; i + 1 < p->num_wavelengths; ++i) {
+    if (!(p->wavelengths[i] < p->wavelengths[i + 1])) {
+      return fail(PAS_ERR_INVALID_ARGUMENT, "wavelengths must be strictly increasing");
+    }
+  }
+  if (!(p->bottom_radius > 0.0) || !(p->top_radius > p->bottom_radius)) {
+    return fail(PAS_ERR_INVALID_ARGUMENT, "need 0 < bottom_radius < top_radius");
+  }
+  if (!(p->length_unit_in_meters > 0.0)) {
+    return fail(PAS_ERR_INVALID_ARGUMENT, "length_unit_in_meters must be positive");
+  }
+  if (!(p->sun_angular_radius > 0.0) || p->sun_angular_radius >= 0.1) {
+    // documented validity limit of the sun-disc approximations (atmosphere/model.h:194-195)
+    return fail(PAS_ERR_INVALID_ARGUMENT, "sun_angular_radius must be in (0, 0.1) rad");
+  }
+  if (p->num_rayleigh_layers > 2 || p->num_mie_layers > 2 || p->num_absorption_layers > 2) {
+    return fail(PAS_ERR_INVALID_ARGUMENT, "at most 2 density layers per profile");
+  }
+  if ((p->num_rayleigh_layers && !p->rayleigh_density) || (p->num_mie_layers && !p->mie_density) ||
+      (p->num_absorption_layers && !p->absorption_density)) {
+    return fail(PAS_ERR_INVALID_ARGUMENT, "missing density layer arrays");
+  }
+  if (!(std::fabs(p->mie_phase_function_g) < 1.0)) {
+    return fail(PAS_ERR_INVALID_ARGUMENT, "|mie_phase_function_g| must be < 1");
+  }
+  if (p->num_precomputed_wavelengths < 1 || p->num_precomputed_wavelengths > 240) {
+    return fail(PAS_ERR_INVALID_ARGUMENT, "num_precomputed_wavelengths must be in [1, 240]");
+  }
+  return PAS_OK;
+}
+
+void split_channels(int total, std::vector<int>* sizes) {
+  static const int kSupported[] = {16, 15, 8, 4, 3, 2, 1};
+  while (total > 0) {
+    for (int s : kSupported) {
+      if (s <= total && pas::channel_count_supported(s)) {
+        sizes->push_back(s);
+        total -= s;
+        break;
+      }
+    }
+  }
+}
+
+struct PhaseTimer {
+  pas_model* m;
+  std::vector<std::pair<std::string, cudaEvent_t>> marks;
+  explicit PhaseTimer(pas_model* model) : m(model) {}
+  void mark(const std::string& name) {
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    cudaEventRecord(e, m->stream);
+    marks.emplace_back(name, e);
+  }
+  void finish() {
+    m->timings.clear();
+    for (size_t i = 1; i < marks.size(); ++i) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, marks[i - 1].second, marks[i].second);
+      m->timings.emplace_back(marks[i].first, ms);
+    }
+    for (auto& mk : marks) cudaEventDestroy(mk.second);
+    marks.clear();
+  }
+};
+
+// keeps a copy of an intermediate (all channels, planar) when capture is on
+pas_status capture_copy(pas_model* m, const std::string& name, const float* src, size_t texels,
+                        int nc, int channel_offset) {
+  if (!m->capture) return PAS_OK;
+  auto& slot = m->captured[name];
+  if (!slot) slot.reset(new DeviceBuffer());
+  PAS_CUDA(slot->ensure(texels * m->total_channels() * sizeof(float)));
+  PAS_CUDA(cudaMemcpyAsync(slot->f() + (size_t)channel_offset * texels, src,
+                           texels * nc * sizeof(float), cudaMemcpyDeviceToDevice, m->stream));
+  return PAS_OK;
+}
+
+__global__ void accumulate_irradiance_kernel(const float* __restrict__ dE, int n, int nc,
+                                             PasSpectrum sp, float* __restrict__ E) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  float4 e = reinterpret_cast<float4*>(E)[t];
+  for (int c = 0; c < nc; ++c) {
+    const float v = dE[(size_t)c * n + t];
+    e.x = fmaf(sp.lum[0][c], v, e.x);
+    e.y = fmaf(sp.lum[1][c], v, e.y);
+    e.z = fmaf(sp.lum[2][c], v, e.z);
+  }
+  reinterpret_cast<float4*>(E)[t] = e;
+}
+
+__global__ void half_to_float_kernel(const __half* __restrict__ src, size_t n, float* __restrict__ dst) {
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) dst[t] = __half2float(src[t]);
+}
+
+pas_status texture_lookup(const pas_model* m, pas_texture which, const DeviceBuffer** buf,
+                          pas_texture_info* info) {
+  pas_texture_info i{};
+  i.channels = 4;
+  i.present = 1;
+  const PasSizes& z = m->geom.sz;
+  switch (which) {
+    case PAS_TEXTURE_TRANSMITTANCE:
+      i.width = z.t_w; i.height = z.t_h; i.depth = 1; i.bytes_per_channel = 4;
+      if (buf) *buf = &m->T_rgba;
+      break;
+    case PAS_TEXTURE_IRRADIANCE:
+      i.width = z.e_w; i.height = z.e_h; i.depth = 1; i.bytes_per_channel = 4;
+      if (buf) *buf = &m->E;
+      break;
+    case PAS_TEXTURE_SCATTERING:
+      i.width = z.nu_n * z.mu_s_n; i.height = z.mu_n; i.depth = z.r_n;
+      i.bytes_per_channel = m->half ? 2 : 4;
+      if (buf) *buf = &m->S;
+      break;
+    case PAS_TEXTURE_SINGLE_MIE:
+      i.width = z.nu_n * z.mu_s_n; i.height = z.mu_n; i.depth = z.r_n;
+      i.bytes_per_channel = m->half ? 2 : 4;
+      i.present = m->combined ? 0 : 1;
+      if (buf) *buf = &m->M;
+      break;
+    default:
+      return fail(PAS_ERR_INVALID_ARGUMENT, "unknown texture id");
+  }
+  if (info) *info = i;
+  return PAS_OK;
+}
+
+// Live intermediate buffers by name (teacher-forced test hooks).
+bool live_buffer(pas_model* m, const std::string& name, float** p, size_t* texels) {
+  if (name == "transmittance") { *p = m->T.f(); *texels = m->n_t(); return true; }
+  if (name == "delta_irradiance") { *p = m->dE.f(); *texels = m->n_e(); return true; }
+  if (name == "delta_rayleigh") { *p = m->dR.f(); *texels = m->n_s(); return true; }
+  if (name == "delta_mie") { *p = m->dM.f(); *texels = m->n_s(); return true; }
+  if (name == "delta_density") { *p = m->dJ.f(); *texels = m->n_s(); return true; }
+  if (name == "delta_multiple") { *p = m->dS.f(); *texels = m->n_s(); return true; }
+  return false;
+}
+
+pas::FinalTables final_tables(pas_model* m, bool accumulate) {
+  pas::FinalTables f{};
+  f.scattering = m->S.p;
+  f.single_mie = m->combined ? nullptr : m->M.p;
+  f.irradiance = m->E.f();
+  f.half_precision = m->half ? 1 : 0;
+  f.accumulate = accumulate ? 1 : 0;
+  return f;
+}
+
+pas_status allocate(pas_model* m) {
+  int max_nc = 0;
+  for (const auto& g : m->groups) max_nc = std::max(max_nc, g.nc);
+  const PasSizes& z = m->geom.sz;
+  PAS_CUDA(m->T.ensure(m->n_t() * max_nc * sizeof(float)));
+  PAS_CUDA(m->T_rgb.ensure(m->n_t() * 3 * sizeof(float)));
+  PAS_CUDA(m->dE.ensure(m->n_e() * max_nc * sizeof(float)));
+  PAS_CUDA(m->dR.ensure(m->n_s() * max_nc * sizeof(float)));
+  PAS_CUDA(m->dM.ensure(m->n_s() * max_nc * sizeof(float)));
+  PAS_CUDA(m->dJ.ensure(m->n_s() * max_nc * sizeof(float)));
+  PAS_CUDA(m->dS.ensure(m->n_s() * max_nc * sizeof(float)));
+  PAS_CUDA(m->dirs.ensure((size_t)z.r_n * PAS_DIR_THETA * sizeof(PasDensityDir)));
+  PAS_CUDA(m->G.ensure((size_t)z.r_n * PAS_DIR_THETA * PAS_MAX_CH * sizeof(float)));
+  PAS_CUDA(m->cR.ensure((size_t)z.r_n * PAS_MAX_CH * sizeof(float)));
+  PAS_CUDA(m->cM.ensure((size_t)z.r_n * PAS_MAX_CH * sizeof(float)));
+  PAS_CUDA(m->S.ensure(m->n_s() * m->s_texel_bytes()));
+  if (!m->combined) PAS_CUDA(m->M.ensure(m->n_s() * m->s_texel_bytes()));
+  PAS_CUDA(m->E.ensure(m->n_e() * 16));
+  PAS_CUDA(m->T_rgba.ensure(m->n_t() * 16));
+  return PAS_OK;
+}
+
+// One phase of Precompute (model.cc:1048-1215) for channel group `gi`.
+pas_status run_phase(pas_model* m, int gi, int phase, int order, bool accumulate) {
+  const PasSpectrum& sp = m->groups[gi];
+  const PasGeometry& g = m->geom;
+  int k0, k1;
+  m->slab(&k0, &k1);
+  pas::FinalTables fin = final_tables(m, accumulate);
+  switch (phase) {
+    case 0:
+      PAS_CUDA(pas::launch_transmittance(g, sp, m->T.f(), m->stream));
+      PAS_CUDA(pas::launch_density_setup(g, sp, m->T.f(), static_cast<PasDensityDir*>(m->dirs.p),
+                                         m->G.f(), m->cR.f(), m->cM.f(), m->stream));
+      m->launches += 2;
+      break;
+    case 1:
+      PAS_CUDA(pas::launch_direct_irradiance(g, sp, m->T.f(), m->dE.f(), fin, m->stream));
+      m->launches += 1;
+      break;
+    case 2:
+      PAS_CUDA(pas::launch_single_scattering(g, sp, m->T.f(), m->dR.f(), m->dM.f(), fin, k0, k1,
+                                             m->stream));
+      m->launches += 1;
+      break;
+    case 3:
+      PAS_CUDA(pas::launch_scattering_density(
+          g, sp, static_cast<const PasDensityDir*>(m->dirs.p), m->G.f(), m->cR.f(), m->cM.f(),
+          m->dR.f(), m->dM.f(), m->dS.f(), m->dE.f(), order, m->dJ.f(), k0, k1, m->stream));
+      m->launches += 1;
+      if (m->world > 1) {
+        // all-gather of the density r-slabs over NVLink: every rank needs every layer its rays
+        // cross in the multiple-scattering pass
+        const size_t lt = m->layer_texels();
+        PAS_NCCL(nccl().GroupStart());
+        const int base = g.sz.r_n / m->world, extra = g.sz.r_n % m->world;
+        for (int c = 0; c < sp.nc; ++c) {
+          float* plane = m->dJ.f() + (size_t)c * m->n_s();
+          if (extra == 0) {
+            PAS_NCCL(nccl().AllGather(plane + (size_t)k0 * lt, plane, (size_t)base * lt, ncclFloat,
+                                      m->comm, m->stream));
+          } else {
+            return fail(PAS_ERR_UNSUPPORTED, "scattering_r must be divisible by the world size");
+          }
+        }
+        PAS_NCCL(nccl().GroupEnd());
+      }
+      break;
+    case 4: {
+      if (m->world > 1) fin.irradiance = nullptr;  // partial sums: accumulate after the all-reduce
+      PAS_CUDA(pas::launch_indirect_irradiance(g, sp, m->dR.f(), m->dM.f(), m->dS.f(), order,
+                                               m->dE.f(), fin, 0, g.sz.e_h, k0, k1, m->stream));
+      m->launches += 1;
+      if (m->world > 1) {
+        PAS_NCCL(nccl().AllReduce(m->dE.f(), m->dE.f(), m->n_e() * sp.nc, ncclFloat, ncclSum,
+                                  m->comm, m->stream));
+        const int n = (int)m->n_e();
+        accumulate_irradiance_kernel<<<(n + 127) / 128, 128, 0, m->stream>>>(m->dE.f(), n, sp.nc, sp,
+                                                                              m->E.f());
+        PAS_CUDA(cudaGetLastError());
+        m->launches += 1;
+      }
+      break;
+    }
+    case 5:
+      PAS_CUDA(pas::launch_multiple_scattering(g, sp, m->T.f(), m->dJ.f(), m->dS.f(), fin, k0, k1,
+                                               m->stream));
+      m->launches += 1;
+      break;
+    default:
+      return fail(PAS_ERR_INVALID_ARGUMENT, "unknown phase");
+  }
+  return PAS_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* pas_last_error(void) { return g_last_error.c_str(); }
+int pas_abi_version(void) { return PAS_B200_ABI_VERSION; }
+
+pas_status pas_model_create(const pas_model_params* p, pas_model** out) {
+  if (out == nullptr) return fail(PAS_ERR_INVALID_ARGUMENT, "out_model is NULL");
+  *out = nullptr;
+  pas_status st = validate(p);
+  if (st != PAS_OK) return st;
+  std::unique_ptr<pas_model> m(new pas_model());
+  const size_t n = p->num_wavelengths;
+  m->wavelengths.assign(p->wavelengths, p->wavelengths + n);
+  m->solar.assign(p->solar_irradiance, p->solar_irradiance + n);
+  m->rayleigh.assign(p->rayleigh_scattering, p->rayleigh_scattering + n);
+  m->mie_sca.assign(p->mie_scattering, p->mie_scattering + n);
+  m->mie_ext.assign(p->mie_extinction, p->mie_extinction + n);
+  m->absorption.assign(p->absorption_extinction, p->absorption_extinction + n);
+  m->albedo.assign(p->ground_albedo, p->ground_albedo + n);
+  m->profile_layers[0].assign(p->rayleigh_density, p->rayleigh_density + p->num_rayleigh_layers);
+  m->profile_layers[1].assign(p->mie_density, p->mie_density + p->num_mie_layers);
+  m->profile_layers[2].assign(p->absorption_density, p->absorption_density + p->num_absorption_layers);
+  m->sun_angular_radius = p->sun_angular_radius;
+  m->bottom = p->bottom_radius;
+  m->top = p->top_radius;
+  m->mie_g = p->mie_phase_function_g;
+  m->max_sun_zenith = p->max_sun_zenith_angle;
+  m->unit = p->length_unit_in_meters;
+  m->num_precomputed_wavelengths = p->num_precomputed_wavelengths;
+  m->combined = p->combine_scattering_textures != 0;
+  m->half = p->half_precision != 0;
+
+  // ---- geometry block, in length units (model.cc:718-734) ----
+  PasGeometry& g = m->geom;
+  auto pick = [](int v, int dflt) { return v > 0 ? v : dflt; };
+  g.sz.t_w = pick(p->sizes.transmittance_width, 256);
+  g.sz.t_h = pick(p->sizes.transmittance_height, 64);
+  g.sz.r_n = pick(p->sizes.scattering_r, 32);
+  g.sz.mu_n = pick(p->sizes.scattering_mu, 128);
+  g.sz.mu_s_n = pick(p->sizes.scattering_mu_s, 32);
+  g.sz.nu_n = pick(p->sizes.scattering_nu, 8);
+  g.sz.e_w = pick(p->sizes.irradiance_width, 64);
+  g.sz.e_h = pick(p->sizes.irradiance_height, 16);
+  if (g.sz.t_w < 2 || g.sz.t_h < 2 || g.sz.r_n < 2 || g.sz.mu_n < 4 || (g.sz.mu_n & 1) ||
+      g.sz.mu_s_n < 2 || g.sz.nu_n < 2 || g.sz.e_w < 2 || g.sz.e_h < 2) {
+    return fail(PAS_ERR_INVALID_ARGUMENT, "table sizes must be >= 2 (scattering_mu even, >= 4)");
+  }
+  if (g.sz.nu_n > PAS_MAX_NU || g.sz.nu_n * g.sz.mu_s_n > 1024 || g.sz.e_w > 1024) {
+    return fail(PAS_ERR_UNSUPPORTED,
+                "supported: scattering_nu <= 16, scattering_nu * scattering_mu_s <= 1024, "
+                "irradiance_width <= 1024");
+  }
+  g.bottom = m->bottom / m->unit;
+  g.top = m->top / m->unit;
+  g.H = std::sqrt(g.top * g.top - g.bottom * g.bottom);
+  g.mu_s_min = std::cos(m->max_sun_zenith);
+  g.sun_angular_radius = m->sun_angular_radius;
+  g.mie_g = m->mie_g;
+  {
+    // "A" of the mu_s mapping (functions.glsl:819-821)
+    const double d_min = g.top - g.bottom, d_max = g.H;
+    const double D = pas::dist_top(g, g.bottom, g.mu_s_min);
+    g.mus_A = (D - d_min) / (d_max - d_min);
+  }
+  for (int pr = 0; pr < 3; ++pr) {
+    // missing layers are zero layers inserted at the front (model.cc:653-666); lengths are divided,
+    // inverse lengths multiplied by the length unit (model.cc:641-650)
+    std::vector<pas_density_layer> ls = m->profile_layers[pr];
+    while (ls.size() < 2) ls.insert(ls.begin(), pas_density_layer{0, 0, 0, 0, 0});
+    for (int l = 0; l < 2; ++l) {
+      g.profiles[pr][l][0] = ls[l].width / m->unit;
+      g.profiles[pr][l][1] = ls[l].exp_term;
+      g.profiles[pr][l][2] = ls[l].exp_scale * m->unit;
+      g.profiles[pr][l][3] = ls[l].linear_term * m->unit;
+      g.profiles[pr][l][4] = ls[l].constant_term;
+    }
+  }
+
+  // ---- channels and luminance matrices (model.cc:907-949) ----
+  const double lam_rgb[3] = {680.0, 550.0, 440.0};
+  if (m->num_precomputed_wavelengths <= 3) {
+    m->lambdas.assign(lam_rgb, lam_rgb + 3);
+    m->lum = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  } else {
+    const int iters = (int)(m->num_precomputed_wavelengths + 2) / 3;
+    const int C = 3 * iters;
+    const double dl = (pas::kCieLambdaMax - pas::kCieLambdaMin) / C;
+    m->lambdas.resize(C);
+    m->lum.assign(3 * (size_t)C, 0.f);
+    for (int j = 0; j < C; ++j) {
+      const double l = pas::kCieLambdaMin + (j + 0.5) * dl;
+      m->lambdas[j] = l;
+      const double xyz[3] = {cie_value(l, 1), cie_value(l, 2), cie_value(l, 3)};
+      for (int a = 0; a < 3; ++a) {
+        // MAX_LUMINOUS_EFFICACY deliberately omitted here (model.cc:926-930)
+        m->lum[(size_t)a * C + j] = static_cast<float>(
+            (pas::kXyzToSrgb[a][0] * xyz[0] + pas::kXyzToSrgb[a][1] * xyz[1] +
+             pas::kXyzToSrgb[a][2] * xyz[2]) * dl);
+      }
+    }
+  }
+  const int C = m->total_channels();
+  std::vector<int> sizes;
+  split_channels(C, &sizes);
+  int off = 0;
+  for (int s : sizes) {
+    m->groups.push_back(make_spectrum(*m, m->lambdas.data() + off, s, m->lum.data(), C, off));
+    m->group_offset.push_back(off);
+    off += s;
+  }
+  m->rgb_spectrum = make_spectrum(*m, lam_rgb, 3, nullptr, 0, 0);
+  // SKY / SUN_SPECTRAL_RADIANCE_TO_LUMINANCE (model.cc:668-686)
+  if (m->num_precomputed_wavelengths > 3) {
+    m->sky_k[0] = m->sky_k[1] = m->sky_k[2] = pas::kMaxLuminousEfficacy;
+  } else {
+    luminance_factors(m->wavelengths, m->solar, -3.0, m->sky_k);
+  }
+  luminance_factors(m->wavelengths, m->solar, 0.0, m->sun_k);
+
+  // ---- device ----
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    return fail(PAS_ERR_CUDA, std::string("no CUDA device available: ") +
+                                  (e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e)));
+  }
+  if (p->device > 0) {
+    m->device = p->device - 1;
+    PAS_CUDA(cudaSetDevice(m->device));
+  } else {
+    PAS_CUDA(cudaGetDevice(&m->device));
+  }
+  PAS_CUDA(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+  st = allocate(m.get());
+  if (st != PAS_OK) return st;
+  *out = m.release();
+  return PAS_OK;
+}
+
+void pas_model_destroy(pas_model* m) {
+  if (m == nullptr) return;
+  cudaSetDevice(m->device);
+  if (m->stream) {
+    cudaStreamSynchronize(m->stream);
+  }
+  if (m->comm != nullptr && nccl().ok) nccl().CommDestroy(m->comm);
+  if (m->stream) cudaStreamDestroy(m->stream);
+  delete m;
+}
+
+pas_status pas_model_init(pas_model* m, unsigned int num_scattering_orders) {
+  if (m == nullptr) return fail(PAS_ERR_INVALID_ARGUMENT, "model is NULL");
+  if (num_scattering_orders < 1) return fail(PAS_ERR_INVALID_ARGUMENT, "need >= 1 scattering order");
+  PAS_CUDA(cudaSetDevice(m->device));
+  m->launches = 0;
+  PhaseTimer timer(m);
+  timer.mark("start");
+  for (size_t gi = 0; gi < m->groups.size(); ++gi) {
+    const bool blend = gi > 0;  // additive blending for batches after the first (model.cc:946-948)
+    const int nc = m->groups[gi].nc, off = m->group_offset[gi];
+    pas_status st;
+    if ((st = run_phase(m, (int)gi, 0, 0, blend)) != PAS_OK) return st;
+    timer.mark("transmittance");
+    if ((st = capture_copy(m, "transmittance", m->T.f(), m->n_t(), nc, off)) != PAS_OK) return st;
+    if ((st = run_phase(m, (int)gi, 1, 0, blend)) != PAS_OK) return st;
+    timer.mark("direct_irradiance");
+    if ((st = capture_copy(m, "delta_irradiance_1", m->dE.f(), m->n_e(), nc, off)) != PAS_OK) return st;
+    if ((st = run_phase(m, (int)gi, 2, 0, blend)) != PAS_OK) return st;
+    timer.mark("single_scattering");
+    if ((st = capture_copy(m, "delta_rayleigh", m->dR.f(), m->n_s(), nc, off)) != PAS_OK) return st;
+    if ((st = capture_copy(m, "delta_mie", m->dM.f(), m->n_s(), nc, off)) != PAS_OK) return st;
+    for (unsigned order = 2; order <= num_scattering_orders; ++order) {
+      const std::string tag = std::to_string(order);
+      if ((st = run_phase(m, (int)gi, 3, (int)order, blend)) != PAS_OK) return st;
+      timer.mark("scattering_density_" + tag);
+      if ((st = capture_copy(m, "delta_density_" + tag, m->dJ.f(), m->n_s(), nc, off)) != PAS_OK) return st;
+      // irradiance from the radiance of the previous order (model.cc:1187-1188)
+      if ((st = run_phase(m, (int)gi, 4, (int)order - 1, blend)) != PAS_OK) return st;
+      timer.mark("indirect_irradiance_" + tag);
+      if ((st = capture_copy(m, "delta_irradiance_" + tag, m->dE.f(), m->n_e(), nc, off)) != PAS_OK) return st;
+      if ((st = run_phase(m, (int)gi, 5, (int)order, blend)) != PAS_OK) return st;
+      timer.mark("multiple_scattering_" + tag);
+      if ((st = capture_copy(m, "delta_multiple_" + tag, m->dS.f(), m->n_s(), nc, off)) != PAS_OK) return st;
+    }
+  }
+  // final transmittance at 680/550/440 nm (model.cc:951-963)
+  if (m->num_precomputed_wavelengths > 3) {
+    PAS_CUDA(pas::launch_transmittance(m->geom, m->rgb_spectrum, m->T_rgb.f(), m->stream));
+    PAS_CUDA(pas::launch_pack_rgba(m->T_rgb.f(), (int)m->n_t(), 3, m->T_rgba.f(), m->stream));
+  } else {
+    PAS_CUDA(pas::launch_pack_rgba(m->T.f(), (int)m->n_t(), 3, m->T_rgba.f(), m->stream));
+    m->launches -= 1;
+  }
+  m->launches += 2;
+  if (m->world > 1) {
+    // every rank ends with the complete scattering table(s)
+    int k0, k1;
+    m->slab(&k0, &k1);
+    const size_t slab_bytes = (size_t)(k1 - k0) * m->layer_texels() * m->s_texel_bytes();
+    PAS_NCCL(nccl().GroupStart());
+    PAS_NCCL(nccl().AllGather(static_cast<char*>(m->S.p) + (size_t)k0 * m->layer_texels() * m->s_texel_bytes(),
+                              m->S.p, slab_bytes, ncclChar, m->comm, m->stream));
+    if (!m->combined) {
+      PAS_NCCL(nccl().AllGather(static_cast<char*>(m->M.p) + (size_t)k0 * m->layer_texels() * m->s_texel_bytes(),
+                                m->M.p, slab_bytes, ncclChar, m->comm, m->stream));
+    }
+    PAS_NCCL(nccl().GroupEnd());
+  }
+  timer.mark("finalize");
+  PAS_CUDA(cudaStreamSynchronize(m->stream));
+  timer.finish();
+  m->initialised = true;
+  return PAS_OK;
+}
+
+pas_status pas_model_texture_info(const pas_model* m, pas_texture which, pas_texture_info* info) {
+  if (m == nullptr || info == nullptr) return fail(PAS_ERR_INVALID_ARGUMENT, "NULL argument");
+  return texture_lookup(m, which, nullptr, info);
+}
+
+pas_status pas_model_texture_device_ptr(const pas_model* m, pas_texture which, const void** ptr) {
+  if (m == nullptr || ptr == nullptr) return fail(PAS_ERR_INVALID_ARGUMENT, "NULL argument");
+  const DeviceBuffer* buf = nullptr;
+  pas_texture_info info;
+  pas_status st = texture_lookup(m, which, &buf, &info);
+  if (st != PAS_OK) return st;
+  if (!info.present) return fail(PAS_ERR_STATE, "this model has no such table");
+  *ptr = buf->p;
+  return PAS_OK;
+}
+
+pas_status pas_model_read_texture(pas_model* m, pas_texture which, int as_float32, void* dst,
+                                  size_t dst_bytes) {
+  if (m == nullptr || dst == nullptr) return fail(PAS_ERR_INVALID_ARGUMENT, "NULL argument");
+  if (!m->initialised) return fail(PAS_ERR_STATE, "pas_model_init has not been called");
+  const DeviceBuffer* buf = nullptr;
+  pas_texture_info info;
+  pas_status st = texture_lookup(m, which, &buf, &info);
+  if (st != PAS_OK) return st;
+  if (!info.present) return fail(PAS_ERR_STATE, "this model has no such table");
+  PAS_CUDA(cudaSetDevice(m->device));
+  const size_t values = (size_t)info.width * info.height * info.depth * 4;
+  const bool convert = as_float32 && info.bytes_per_channel == 2;
+  const size_t need = values * (convert || info.bytes_per_channel == 4 ? 4 : 2);
+  if (dst_bytes != need) {
+    return fail(PAS_ERR_INVALID_ARGUMENT, "dst_bytes is " + std::to_string(dst_bytes) + ", table needs " +
+                                              std::to_string(need));
+  }
+  const void* src = buf->p;
+  if (convert) {
+    PAS_CUDA(m->scratch.ensure(values * sizeof(float)));
+    half_to_float_kernel<<<(unsigned)((values + 255) / 256), 256, 0, m->stream>>>(
+        static_cast<const __half*>(buf->p), values, m->scratch.f());
+    PAS_CUDA(cudaGetLastError());
+    src = m->scratch.p;
+  }
+  PAS_CUDA(cudaMemcpyAsync(dst, src, need, cudaMemcpyDeviceToHost, m->stream));
+  PAS_CUDA(cudaStreamSynchronize(m->stream));
+  return PAS_OK;
+}
+
+pas_status pas_model_save_dat(pas_model* m, const char* directory) {
+  if (m == nullptr || directory == nullptr) return fail(PAS_ERR_INVALID_ARGUMENT, "NULL argument");
+  static const struct { pas_texture id; const char* file; } kFiles[] = {
+      {PAS_TEXTURE_TRANSMITTANCE, "transmittance.dat"},
+      {PAS_TEXTURE_SCATTERING, "scattering.dat"},
+      {PAS_TEXTURE_IRRADIANCE, "irradiance.dat"},
+      {PAS_TEXTURE_SINGLE_MIE, "single_mie_scattering.dat"}};
+  for (const auto& f : kFiles) {
+    pas_texture_info info;
+    pas_status st = texture_lookup(m, f.id, nullptr, &info);
+    if (st != PAS_OK) return st;
+    if (!info.present) continue;
+    std::vector<float> host((size_t)info.width * info.height * info.depth * 4);
+    st = pas_model_read_texture(m, f.id, 1, host.data(), host.size() * sizeof(float));
+    if (st != PAS_OK) return st;
+    const std::string path = std::string(directory) + "/" + f.file;
+    std::ofstream out(path, std::ios::binary);
+    out.write(reinterpret_cast<const char*>(host.data()), host.size() * sizeof(float));
+    if (!out) return fail(PAS_ERR_IO, "cannot write " + path);
+  }
+  return PAS_OK;
+}
+
+pas_status pas_model_luminance_factors(const pas_model* m, double* out6) {
+  if (m == nullptr || out6 == nullptr) return fail(PAS_ERR_INVALID_ARGUMENT, "NULL argument");
+  for (int a = 0; a < 3; ++a) {
+    out6[a] = m->sky_k[a];
+    out6[3 + a] = m->sun_k[a];
+  }
+  return PAS_OK;
+}
+
+pas_status pas_convert_spectrum_to_linear_srgb(size_t n, const double* wavelengths,
+                                               const double* spectrum, double* r, double* g,
+                                               double* b) {
+  if (n < 1 || !wavelengths || !spectrum || !r || !g || !b) {
+    return fail(PAS_ERR_INVALID_ARGUMENT, "NULL argument");
+  }
+  const std::vector<double> wl(wavelengths, wavelengths + n), sp(spectrum, spectrum + n);
+  double xyz[3] = {0, 0, 0};
+  for (int lambda = 360; lambda < 830; ++lambda) {
+    const double v = interpolate(wl, sp, lambda);
+    for (int a = 0; a < 3; ++a) xyz[a] += cie_value(lambda, a + 1) * v;
+  }
+  double* out[3] = {r, g, b};
+  for (int a = 0; a < 3; ++a) {
+    *out[a] = pas::kMaxLuminousEfficacy * (pas::kXyzToSrgb[a][0] * xyz[0] + pas::kXyzToSrgb[a][1] * xyz[1] +
+                                           pas::kXyzToSrgb[a][2] * xyz[2]);
+  }
+  return PAS_OK;
+}
+
+pas_status pas_model_channels(const pas_model* m, int* num_channels, double* lambdas) {
+  if (m == nullptr || num_channels == nullptr) return fail(PAS_ERR_INVALID_ARGUMENT, "NULL argument");
+  *num_channels = m->total_channels();
+  if (lambdas) std::copy(m->lambdas.begin(), m->lambdas.end(), lambdas);
+  return PAS_OK;
+}
+
+pas_status pas_model_luminance_matrix(const pas_model* m, float* out) {
+  if (m == nullptr || out == nullptr) return fail(PAS_ERR_INVALID_ARGUMENT, "NULL argument");
+  std::copy(m->lum.begin(), m->lum.end(), out);
+  return PAS_OK;
+}
+
+pas_status pas_model_set_capture(pas_model* m, int enabled) {
+  if (m == nullptr) return fail(PAS_ERR_INVALID_ARGUMENT, "model is NULL");
+  m->capture = enabled != 0;
+  if (!m->capture) m->captured.clear();
+  return PAS_OK;
+}
+
+pas_status pas_model_read_intermediate(pas_model* m, const char* name, float* dst, size_t* num_floats) {
+  if (m == nullptr || name == nullptr || num_floats == nullptr) {
+    return fail(PAS_ERR_INVALID_ARGUMENT, "NULL argument");
+  }
+  PAS_CUDA(cudaSetDevice(m->device));
+  const float* src = nullptr;
+  size_t count = 0;
+  auto it = m->captured.find(name);
+  float* live = nullptr;
+  size_t texels = 0;
+  if (live_buffer(m, name, &live, &texels)) {
+    src = live;
+    count = texels * m->groups[0].nc;
+  } else if (it != m->captured.end()) {
+    src = it->second->f();
+    count = it->second->bytes / sizeof(float);
+  } else {
+    return fail(PAS_ERR_STATE, std::string("no intermediate named '") + name + "' (capture enabled?)");
+  }
+  if (dst == nullptr) {
+    *num_floats = count;
+    return PAS_OK;
+  }
+  if (*num_floats < count) return fail(PAS_ERR_INVALID_ARGUMENT, "destination too small");
+  PAS_CUDA(cudaMemcpyAsync(dst, src, count * sizeof(float), cudaMemcpyDeviceToHost, m->stream));
+  PAS_CUDA(cudaStreamSynchronize(m->stream));
+  *num_floats = count;
+  return PAS_OK;
+}
+
+pas_status pas_model_write_intermediate(pas_model* m, const char* name, const float* src,
+                                        size_t num_floats) {
+  if (m == nullptr || name == nullptr || src == nullptr) return fail(PAS_ERR_INVALID_ARGUMENT, "NULL argument");
+  PAS_CUDA(cudaSetDevice(m->device));
+  float* live = nullptr;
+  size_t texels = 0;
+  if (!live_buffer(m, name, &live, &texels)) return fail(PAS_ERR_INVALID_ARGUMENT, "unknown live buffer");
+  if (num_floats != texels * m->groups[0].nc) {
+    return fail(PAS_ERR_INVALID_ARGUMENT, "expected " + std::to_string(texels * m->groups[0].nc) + " floats");
+  }
+  PAS_CUDA(cudaMemcpyAsync(live, src, num_floats * sizeof(float), cudaMemcpyHostToDevice, m->stream));
+  PAS_CUDA(cudaStreamSynchronize(m->stream));
+  return PAS_OK;
+}
+
+pas_status pas_model_run_phase(pas_model* m, int phase, int order) {
+  if (m == nullptr) return fail(PAS_ERR_INVALID_ARGUMENT, "model is NULL");
+  if (m->groups.size() != 1) return fail(PAS_ERR_UNSUPPORTED, "single passes need <= 16 channels");
+  PAS_CUDA(cudaSetDevice(m->device));
+  pas_status st = run_phase(m, 0, phase, order, false);
+  if (st != PAS_OK) return st;
+  PAS_CUDA(cudaStreamSynchronize(m->stream));
+  return PAS_OK;
+}
+
+pas_status pas_model_last_timings(const pas_model* m, int* count, const char** names, float* ms) {
+  if (m == nullptr || count == nullptr) return fail(PAS_ERR_INVALID_ARGUMENT, "NULL argument");
+  const int cap = *count;
+  *count = (int)m->timings.size();
+  for (int i = 0; i < cap && i < (int)m->timings.size(); ++i) {
+    if (names) names[i] = m->timings[i].first.c_str();
+    if (ms) ms[i] = m->timings[i].second;
+  }
+  return PAS_OK;
+}
+
+pas_status pas_model_last_launch_count(const pas_model* m, int* launches) {
+  if (m == nullptr || launches == nullptr) return fail(PAS_ERR_INVALID_ARGUMENT, "NULL argument");
+  *launches = m->launches;
+  return PAS_OK;
+}
+
+pas_status pas_nccl_unique_id(void* id_bytes) {
+  if (id_bytes == nullptr) return fail(PAS_ERR_INVALID_ARGUMENT, "NULL argument");
+  if (!nccl().ok) return fail(PAS_ERR_NCCL, "libnccl.so.2 could not be loaded");
+  static_assert(sizeof(ncclUniqueId) == PAS_NCCL_UNIQUE_ID_BYTES, "ncclUniqueId size");
+  ncclUniqueId id;
+  PAS_NCCL(nccl().GetUniqueId(&id));
+  std::memcpy(id_bytes, &id, sizeof id);
+  return PAS_OK;
+}
+
+pas_status pas_model_attach_world(pas_model* m, int rank, int world_size, const void* id_bytes) {
+  if (m == nullptr) return fail(PAS_ERR_INVALID_ARGUMENT, "model is NULL");
+  if (world_size < 1 || rank < 0 || rank >= world_size) {
+    return fail(PAS_ERR_INVALID_ARGUMENT, "bad rank / world size");
+  }
+  if (world_size == 1) {
+    m->rank = 0;
+    m->world = 1;
+    return PAS_OK;
+  }
+  if (id_bytes == nullptr) return fail(PAS_ERR_INVALID_ARGUMENT, "NULL unique id");
+  if (m->geom.sz.r_n % world_size != 0) {
+    return fail(PAS_ERR_UNSUPPORTED, "scattering_r must be divisible by the world size");
+  }
+  if (!nccl().ok) return fail(PAS_ERR_NCCL, "libnccl.so.2 could not be loaded");
+  PAS_CUDA(cudaSetDevice(m->device));
+  ncclUniqueId id;
+  std::memcpy(&id, id_bytes, sizeof id);
+  PAS_NCCL(nccl().CommInitRank(&m->comm, world_size, id, rank));
+  m->rank = rank;
+  m->world = world_size;
+  return PAS_OK;
+}
+
+}  // extern "C"
+
+// ---- GLSL source of the rendering shader (atmosphere/model.cc:691-744, 769-772) -------------------
+namespace {
+
+std::string glsl_number(double v) {
+  // full float precision (the reference prints 6 decimals through std::to_string,
+  // model.cc:636-652; the tables here are computed from the exact values, so the renderer gets them too)
+  char buf[64];
+  std::snprintf(buf, sizeof buf, "%.9g", v);
+  std::string t(buf);
+  if (t.find_first_of(".eE") == std::string::npos) t += ".0";
+  return t;
+}
+
+std::string glsl_vec3(const pas_model& m, const std::vector<double>& v, double scale) {
+  const double lam[3] = {680.0, 550.0, 440.0};
+  std::string t = "vec3(";
+  for (int a = 0; a < 3; ++a) {
+    t += glsl_number(interpolate(m.wavelengths, v, lam[a]) * scale);
+    t += a < 2 ? "," : ")";
+  }
+  return t;
+}
+
+std::string glsl_profile(const PasGeometry& g, int profile) {
+  std::string t = "DensityProfile(DensityProfileLayer[2](";
+  for (int l = 0; l < 2; ++l) {
+    t += "DensityProfileLayer(";
+    for (int f = 0; f < 5; ++f) {
+      t += glsl_number(g.profiles[profile][l][f]);
+      t += f < 4 ? "," : ")";
+    }
+    t += l == 0 ? "," : "))";
+  }
+  return t;
+}
+
+bool read_text(const std::string& path, std::string* out) {
+  std::ifstream in(path, std::ios::binary);
+  if (!in) return false;
+  std::stringstream ss;
+  ss << in.rdbuf();
+  *out = ss.str();
+  return true;
+}
+
+// One GLSL wrapper per public entry point of the rendering API (the functions the demo and the
+// integration test call, atmosphere/demo/demo.glsl:304-380): each forwards to the function of the
+// same base name in functions.glsl with the ATMOSPHERE constant and the table samplers bound.
+struct ApiEntry {
+  const char* result;      // return type
+  const char* name;        // exported name
+  const char* params;      // parameter list
+  const char* callee;      // functions.glsl function
+  const char* tables;      // sampler arguments
+  const char* args;        // forwarded arguments
+  const char* out_scale;   // constant applied to the `out` sky irradiance, or ""
+  const char* scale;       // constant applied to the result, or ""
+  bool radiance_only;      // only when RADIANCE_API_ENABLED
+};
+
+std::string api_wrappers() {
+  static const char kSkyParams[] =
+      "Position camera, Direction view_ray, Length shadow_length, Direction sun_direction, "
+      "out DimensionlessSpectrum transmittance";
+  static const char kPointParams[] =
+      "Position camera, Position point, Length shadow_length, Direction sun_direction, "
+      "out DimensionlessSpectrum transmittance";
+  static const char kIrrParams[] =
+      "Position p, Direction normal, Direction sun_direction, out IrradianceSpectrum sky_irradiance";
+  static const char kScatTables[] =
+      "transmittance_texture, scattering_texture, single_mie_scattering_texture";
+  static const char kIrrTables[] = "transmittance_texture, irradiance_texture";
+  static const ApiEntry kApi[] = {
+      {"RadianceSpectrum", "GetSkyRadiance", kSkyParams, "GetSkyRadiance", kScatTables,
+       "camera, view_ray, shadow_length, sun_direction, transmittance", "", "", true},
+      {"RadianceSpectrum", "GetSkyRadianceToPoint", kPointParams, "GetSkyRadianceToPoint", kScatTables,
+       "camera, point, shadow_length, sun_direction, transmittance", "", "", true},
+      {"IrradianceSpectrum", "GetSunAndSkyIrradiance", kIrrParams, "GetSunAndSkyIrradiance", kIrrTables,
+       "p, normal, sun_direction, sky_irradiance", "", "", true},
+      {"Luminance3", "GetSkyLuminance", kSkyParams, "GetSkyRadiance", kScatTables,
+       "camera, view_ray, shadow_length, sun_direction, transmittance", "",
+       "SKY_SPECTRAL_RADIANCE_TO_LUMINANCE", false},
+      {"Luminance3", "GetSkyLuminanceToPoint", kPointParams, "GetSkyRadianceToPoint", kScatTables,
+       "camera, point, shadow_length, sun_direction, transmittance", "",
+       "SKY_SPECTRAL_RADIANCE_TO_LUMINANCE", false},
+      {"Illuminance3", "GetSunAndSkyIlluminance", kIrrParams, "GetSunAndSkyIrradiance", kIrrTables,
+       "p, normal, sun_direction, sky_irradiance", "SKY_SPECTRAL_RADIANCE_TO_LUMINANCE",
+       "SUN_SPECTRAL_RADIANCE_TO_LUMINANCE", false},
+  };
+  static const char kSolar[] =
+      "ATMOSPHERE.solar_irradiance / (PI * ATMOSPHERE.sun_angular_radius * ATMOSPHERE.sun_angular_radius)";
+  std::string radiance, luminance;
+  radiance += std::string("RadianceSpectrum GetSolarRadiance() {\n  return ") + kSolar + ";\n}\n";
+  luminance += std::string("Luminance3 GetSolarLuminance() {\n  return ") + kSolar +
+               " * SUN_SPECTRAL_RADIANCE_TO_LUMINANCE;\n}\n";
+  for (const ApiEntry& e : kApi) {
+    std::string f = std::string(e.result) + " " + e.name + "(" + e.params + ") {\n";
+    f += std::string("  ") + e.result + " result = " + e.callee + "(ATMOSPHERE, " + e.tables + ", " +
+         e.args + ")" + (e.scale[0] ? std::string(" * ") + e.scale : std::string()) + ";\n";
+    if (e.out_scale[0]) f += std::string("  sky_irradiance *= ") + e.out_scale + ";\n";
+    f += "  return result;\n}\n";
+    (e.radiance_only ? radiance : luminance) += f;
+  }
+  return "uniform sampler2D transmittance_texture;\nuniform sampler3D scattering_texture;\n"
+         "uniform sampler3D single_mie_scattering_texture;\nuniform sampler2D irradiance_texture;\n"
+         "#ifdef RADIANCE_API_ENABLED\n" + radiance + "#endif\n" + luminance;
+}
+
+}  // namespace
+
+extern "C" pas_status pas_model_shader_source(const pas_model* m, const char* glsl_directory,
+                                              char* buffer, size_t* size) {
+  if (m == nullptr || glsl_directory == nullptr || size == nullptr) {
+    return fail(PAS_ERR_INVALID_ARGUMENT, "NULL argument");
+  }
+  std::string definitions, functions;
+  const std::string dir(glsl_directory);
+  if (!read_text(dir + "/definitions.glsl", &definitions) || !read_text(dir + "/functions.glsl", &functions)) {
+    return fail(PAS_ERR_IO, "cannot read definitions.glsl / functions.glsl in " + dir);
+  }
+  const PasGeometry& g = m->geom;
+  std::string src = "#version 330\n#define IN(x) const in x\n#define OUT(x) out x\n"
+                    "#define TEMPLATE(x)\n#define TEMPLATE_ARGUMENT(x)\n#define assert(x)\n";
+  const std::pair<const char*, int> kSizes[] = {
+      {"TRANSMITTANCE_TEXTURE_WIDTH", g.sz.t_w}, {"TRANSMITTANCE_TEXTURE_HEIGHT", g.sz.t_h},
+      {"SCATTERING_TEXTURE_R_SIZE", g.sz.r_n}, {"SCATTERING_TEXTURE_MU_SIZE", g.sz.mu_n},
+      {"SCATTERING_TEXTURE_MU_S_SIZE", g.sz.mu_s_n}, {"SCATTERING_TEXTURE_NU_SIZE", g.sz.nu_n},
+      {"IRRADIANCE_TEXTURE_WIDTH", g.sz.e_w}, {"IRRADIANCE_TEXTURE_HEIGHT", g.sz.e_h}};
+  for (const auto& kv : kSizes) {
+    src += std::string("const int ") + kv.first + " = " + std::to_string(kv.second) + ";\n";
+  }
+  if (m->combined) src += "#define COMBINED_SCATTERING_TEXTURES\n";
+  src += definitions;
+  // field order of AtmosphereParameters (atmosphere/definitions.glsl:213-255)
+  src += "const AtmosphereParameters ATMOSPHERE = AtmosphereParameters(\n";
+  src += glsl_vec3(*m, m->solar, 1.0) + ",\n" + glsl_number(m->sun_angular_radius) + ",\n" +
+         glsl_number(g.bottom) + ",\n" + glsl_number(g.top) + ",\n" + glsl_profile(g, 0) + ",\n" +
+         glsl_vec3(*m, m->rayleigh, m->unit) + ",\n" + glsl_profile(g, 1) + ",\n" +
+         glsl_vec3(*m, m->mie_sca, m->unit) + ",\n" + glsl_vec3(*m, m->mie_ext, m->unit) + ",\n" +
+         glsl_number(m->mie_g) + ",\n" + glsl_profile(g, 2) + ",\n" +
+         glsl_vec3(*m, m->absorption, m->unit) + ",\n" + glsl_vec3(*m, m->albedo, 1.0) + ",\n" +
+         glsl_number(g.mu_s_min) + ");\n";
+  auto vec3_of = [](const double* k) {
+    return "vec3(" + glsl_number(k[0]) + "," + glsl_number(k[1]) + "," + glsl_number(k[2]) + ")";
+  };
+  src += "const vec3 SKY_SPECTRAL_RADIANCE_TO_LUMINANCE = " + vec3_of(m->sky_k) + ";\n";
+  src += "const vec3 SUN_SPECTRAL_RADIANCE_TO_LUMINANCE = " + vec3_of(m->sun_k) + ";\n";
+  src += functions;
+  if (m->num_precomputed_wavelengths <= 3) src += "#define RADIANCE_API_ENABLED\n";
+  src += api_wrappers();
+  const size_t need = src.size() + 1;
+  if (buffer == nullptr) {
+    *size = need;
+    return PAS_OK;
+  }
+  if (*size < need) return fail(PAS_ERR_INVALID_ARGUMENT, "buffer too small");
+  std::memcpy(buffer, src.c_str(), need);
+  *size = need;
+  return PAS_OK;
+}

@@ -1,0 +1,325 @@
+"""Python mirror of the reference's ``atmosphere::Model`` (atmosphere/model.h:180-337) over the C ABI
+of libpas_b200.so (include/pas_b200.h). Same constructor arguments, same ``Init``; the tables come
+back as numpy arrays instead of GL texture names. This module is plumbing only: every table is
+computed by the CUDA kernels behind ``pas_model_init`` and there is no CPU fallback -- if the
+library is missing or no GPU is present the constructor raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+
+from .atmospheres import AtmosphereSpec, DensityProfileLayer
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpas_b200.so")
+
+TEXTURE_TRANSMITTANCE, TEXTURE_SCATTERING, TEXTURE_IRRADIANCE, TEXTURE_SINGLE_MIE = 0, 1, 2, 3
+PHASES = {"transmittance": 0, "direct_irradiance": 1, "single_scattering": 2,
+          "scattering_density": 3, "indirect_irradiance": 4, "multiple_scattering": 5}
+
+
+class PasError(RuntimeError):
+    def __init__(self, status: int, message: str):
+        super().__init__(f"pas_b200 status {status}: {message}")
+        self.status = status
+
+
+class _Layer(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_double) for n in
+                ("width", "exp_term", "exp_scale", "linear_term", "constant_term")]
+
+
+class _Sizes(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int) for n in
+                ("transmittance_width", "transmittance_height", "scattering_r", "scattering_mu",
+                 "scattering_mu_s", "scattering_nu", "irradiance_width", "irradiance_height")]
+
+
+_DP = ctypes.POINTER(ctypes.c_double)
+_LP = ctypes.POINTER(_Layer)
+
+
+class _Params(ctypes.Structure):
+    _fields_ = [
+        ("num_wavelengths", ctypes.c_size_t), ("wavelengths", _DP), ("solar_irradiance", _DP),
+        ("sun_angular_radius", ctypes.c_double), ("bottom_radius", ctypes.c_double),
+        ("top_radius", ctypes.c_double),
+        ("num_rayleigh_layers", ctypes.c_size_t), ("rayleigh_density", _LP),
+        ("rayleigh_scattering", _DP),
+        ("num_mie_layers", ctypes.c_size_t), ("mie_density", _LP), ("mie_scattering", _DP),
+        ("mie_extinction", _DP), ("mie_phase_function_g", ctypes.c_double),
+        ("num_absorption_layers", ctypes.c_size_t), ("absorption_density", _LP),
+        ("absorption_extinction", _DP), ("ground_albedo", _DP),
+        ("max_sun_zenith_angle", ctypes.c_double), ("length_unit_in_meters", ctypes.c_double),
+        ("num_precomputed_wavelengths", ctypes.c_uint), ("combine_scattering_textures", ctypes.c_int),
+        ("half_precision", ctypes.c_int), ("sizes", _Sizes), ("device", ctypes.c_int)]
+
+
+class _TextureInfo(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int) for n in
+                ("width", "height", "depth", "channels", "bytes_per_channel", "present")]
+
+
+_lib = None
+
+
+def load_library() -> ctypes.CDLL:
+    """Loads the in-tree C-ABI library. Fails loudly if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise FileNotFoundError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; "
+                f"g.build()'` (nvcc, sm_100a). There is no CPU fallback.")
+        lib = ctypes.CDLL(LIB_PATH)
+        lib.pas_last_error.restype = ctypes.c_char_p
+        lib.pas_model_create.argtypes = [ctypes.POINTER(_Params), ctypes.POINTER(ctypes.c_void_p)]
+        lib.pas_model_destroy.argtypes = [ctypes.c_void_p]
+        lib.pas_model_init.argtypes = [ctypes.c_void_p, ctypes.c_uint]
+        lib.pas_model_texture_info.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(_TextureInfo)]
+        lib.pas_model_texture_device_ptr.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]
+        lib.pas_model_read_texture.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t]
+        lib.pas_model_save_dat.argtypes = [ctypes.c_void_p, ctypes.c_char_p]
+        lib.pas_model_shader_source.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_void_p, ctypes.POINTER(ctypes.c_size_t)]
+        lib.pas_model_luminance_factors.argtypes = [ctypes.c_void_p, _DP]
+        lib.pas_convert_spectrum_to_linear_srgb.argtypes = [ctypes.c_size_t, _DP, _DP, _DP, _DP, _DP]
+        lib.pas_model_channels.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int), _DP]
+        lib.pas_model_luminance_matrix.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_float)]
+        lib.pas_model_set_capture.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        lib.pas_model_read_intermediate.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_void_p, ctypes.POINTER(ctypes.c_size_t)]
+        lib.pas_model_write_intermediate.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_void_p, ctypes.c_size_t]
+        lib.pas_model_run_phase.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
+        lib.pas_model_last_timings.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(ctypes.c_float)]
+        lib.pas_model_last_launch_count.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int)]
+        lib.pas_nccl_unique_id.argtypes = [ctypes.c_void_p]
+        lib.pas_model_attach_world.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+        _lib = lib
+    return _lib
+
+
+def _check(status: int):
+    if status != 0:
+        raise PasError(status, load_library().pas_last_error().decode("utf-8", "replace"))
+
+
+def _darr(v: Sequence[float]):
+    a = np.ascontiguousarray(np.asarray(v, dtype=np.float64))
+    return a, a.ctypes.data_as(_DP)
+
+
+def _layers(layers: Sequence[DensityProfileLayer]):
+    arr = (_Layer * max(len(layers), 1))()
+    for i, l in enumerate(layers):
+        arr[i] = _Layer(*l.astuple())
+    return arr
+
+
+def nccl_unique_id() -> bytes:
+    buf = ctypes.create_string_buffer(128)
+    _check(load_library().pas_nccl_unique_id(buf))
+    return buf.raw
+
+
+def convert_spectrum_to_linear_srgb(wavelengths: Sequence[float], spectrum: Sequence[float]):
+    """atmosphere::Model::ConvertSpectrumToLinearSrgb (atmosphere/model.cc:1020-1040)."""
+    w, wp = _darr(wavelengths)
+    s, sp = _darr(spectrum)
+    r, g, b = ctypes.c_double(), ctypes.c_double(), ctypes.c_double()
+    _check(load_library().pas_convert_spectrum_to_linear_srgb(
+        len(w), wp, sp, ctypes.byref(r), ctypes.byref(g), ctypes.byref(b)))
+    return r.value, g.value, b.value
+
+
+class Model:
+    """Same 19 constructor arguments as atmosphere::Model (atmosphere/model.h:182-281), plus the
+    run-time extensions of the C ABI (`sizes`, `device`)."""
+
+    kLambdaR, kLambdaG, kLambdaB = 680.0, 550.0, 440.0
+
+    def __init__(self, wavelengths, solar_irradiance, sun_angular_radius, bottom_radius, top_radius,
+                 rayleigh_density, rayleigh_scattering, mie_density, mie_scattering, mie_extinction,
+                 mie_phase_function_g, absorption_density, absorption_extinction, ground_albedo,
+                 max_sun_zenith_angle, length_unit_in_meters, num_precomputed_wavelengths,
+                 combine_scattering_textures, half_precision, *, sizes: Optional[Dict[str, int]] = None,
+                 device: Optional[int] = None):
+        self._lib = load_library()
+        self._h = ctypes.c_void_p()
+        keep = []
+        p = _Params()
+        p.num_wavelengths = len(wavelengths)
+        for name, v in (("wavelengths", wavelengths), ("solar_irradiance", solar_irradiance),
+                        ("rayleigh_scattering", rayleigh_scattering), ("mie_scattering", mie_scattering),
+                        ("mie_extinction", mie_extinction),
+                        ("absorption_extinction", absorption_extinction), ("ground_albedo", ground_albedo)):
+            if len(v) != len(wavelengths):
+                raise ValueError(f"{name} must have one value per wavelength")  # model.cc:539
+            a, ptr = _darr(v)
+            keep.append(a)
+            setattr(p, name, ptr)
+        p.sun_angular_radius, p.bottom_radius, p.top_radius = sun_angular_radius, bottom_radius, top_radius
+        for name, layers in (("rayleigh", rayleigh_density), ("mie", mie_density),
+                             ("absorption", absorption_density)):
+            arr = _layers(layers)
+            keep.append(arr)
+            setattr(p, f"num_{name}_layers", len(layers))
+            setattr(p, f"{name}_density", ctypes.cast(arr, _LP))
+        p.mie_phase_function_g = mie_phase_function_g
+        p.max_sun_zenith_angle, p.length_unit_in_meters = max_sun_zenith_angle, length_unit_in_meters
+        p.num_precomputed_wavelengths = int(num_precomputed_wavelengths)
+        p.combine_scattering_textures = int(bool(combine_scattering_textures))
+        p.half_precision = int(bool(half_precision))
+        for k, v in (sizes or {}).items():
+            setattr(p.sizes, k, int(v))
+        p.device = 0 if device is None else device + 1
+        _check(self._lib.pas_model_create(ctypes.byref(p), ctypes.byref(self._h)))
+        self.half_precision = bool(half_precision)
+        self.combine_scattering_textures = bool(combine_scattering_textures)
+
+    @classmethod
+    def from_spec(cls, spec: AtmosphereSpec, **kw) -> "Model":
+        return cls(spec.wavelengths, spec.solar_irradiance, spec.sun_angular_radius, spec.bottom_radius,
+                   spec.top_radius, spec.rayleigh_density, spec.rayleigh_scattering, spec.mie_density,
+                   spec.mie_scattering, spec.mie_extinction, spec.mie_phase_function_g,
+                   spec.absorption_density, spec.absorption_extinction, spec.ground_albedo,
+                   spec.max_sun_zenith_angle, spec.length_unit_in_meters,
+                   spec.num_precomputed_wavelengths, spec.combine_scattering_textures,
+                   spec.half_precision, **kw)
+
+    # -- lifetime ------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.pas_model_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- the reference API -----------------------------------------------------------------------
+    def Init(self, num_scattering_orders: int = 4) -> None:
+        """atmosphere::Model::Init (atmosphere/model.cc:866-975)."""
+        _check(self._lib.pas_model_init(self._h, int(num_scattering_orders)))
+
+    def GetShaderSource(self, glsl_directory: str) -> str:
+        """The source atmosphere::Model::shader() compiles (atmosphere/model.cc:691-744, 769-772)."""
+        size = ctypes.c_size_t(0)
+        _check(self._lib.pas_model_shader_source(self._h, glsl_directory.encode(), None, ctypes.byref(size)))
+        buf = ctypes.create_string_buffer(size.value)
+        _check(self._lib.pas_model_shader_source(self._h, glsl_directory.encode(), buf, ctypes.byref(size)))
+        return buf.value.decode()
+
+    # -- tables ----------------------------------------------------------------------------------
+    def texture_info(self, which: int) -> _TextureInfo:
+        info = _TextureInfo()
+        _check(self._lib.pas_model_texture_info(self._h, which, ctypes.byref(info)))
+        return info
+
+    def texture(self, which: int, as_float32: bool = True, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """RGBA texels, shape (depth, height, width, 4) (2-D tables: (height, width, 4))."""
+        info = self.texture_info(which)
+        if not info.present:
+            raise PasError(5, "this model has no such table")
+        dtype = np.float32 if (as_float32 or info.bytes_per_channel == 4) else np.float16
+        shape = ((info.depth,) if info.depth > 1 else ()) + (info.height, info.width, 4)
+        if out is None:
+            out = np.empty(shape, dtype=dtype)
+        assert out.dtype == dtype and out.flags["C_CONTIGUOUS"] and out.size == int(np.prod(shape))
+        _check(self._lib.pas_model_read_texture(self._h, which, int(as_float32), out.ctypes.data, out.nbytes))
+        return out.reshape(shape)
+
+    def device_ptr(self, which: int) -> int:
+        p = ctypes.c_void_p()
+        _check(self._lib.pas_model_texture_device_ptr(self._h, which, ctypes.byref(p)))
+        return p.value
+
+    @property
+    def transmittance(self):
+        return self.texture(TEXTURE_TRANSMITTANCE)
+
+    @property
+    def scattering(self):
+        return self.texture(TEXTURE_SCATTERING)
+
+    @property
+    def irradiance(self):
+        return self.texture(TEXTURE_IRRADIANCE)
+
+    @property
+    def single_mie_scattering(self):
+        return self.texture(TEXTURE_SINGLE_MIE)
+
+    def save_dat(self, directory: str) -> None:
+        _check(self._lib.pas_model_save_dat(self._h, directory.encode()))
+
+    # -- introspection ---------------------------------------------------------------------------
+    def channels(self) -> List[float]:
+        n = ctypes.c_int()
+        _check(self._lib.pas_model_channels(self._h, ctypes.byref(n), None))
+        lam = (ctypes.c_double * n.value)()
+        _check(self._lib.pas_model_channels(self._h, ctypes.byref(n), lam))
+        return list(lam)
+
+    def luminance_matrix(self) -> np.ndarray:
+        c = len(self.channels())
+        out = np.empty((3, c), dtype=np.float32)
+        _check(self._lib.pas_model_luminance_matrix(self._h, out.ctypes.data_as(ctypes.POINTER(ctypes.c_float))))
+        return out
+
+    def luminance_factors(self):
+        out = (ctypes.c_double * 6)()
+        _check(self._lib.pas_model_luminance_factors(self._h, out))
+        return list(out[:3]), list(out[3:])
+
+    def set_capture(self, enabled: bool) -> None:
+        _check(self._lib.pas_model_set_capture(self._h, int(enabled)))
+
+    def _table_shape(self, name: str):
+        t, s, e = (self.texture_info(i) for i in (TEXTURE_TRANSMITTANCE, TEXTURE_SCATTERING, TEXTURE_IRRADIANCE))
+        if name.startswith("transmittance"):
+            return (t.height, t.width)
+        if name.startswith("delta_irradiance"):
+            return (e.height, e.width)
+        return (s.depth, s.height, s.width)
+
+    def intermediate(self, name: str) -> np.ndarray:
+        """Planar per-channel copy [C, ...] of an intermediate (needs set_capture(True) before Init,
+        or one of the live-buffer names after run_phase)."""
+        n = ctypes.c_size_t(0)
+        _check(self._lib.pas_model_read_intermediate(self._h, name.encode(), None, ctypes.byref(n)))
+        out = np.empty(n.value, dtype=np.float32)
+        _check(self._lib.pas_model_read_intermediate(self._h, name.encode(), out.ctypes.data, ctypes.byref(n)))
+        shape = self._table_shape(name)
+        return out.reshape((-1,) + shape)
+
+    def write_intermediate(self, name: str, array: np.ndarray) -> None:
+        a = np.ascontiguousarray(array, dtype=np.float32)
+        _check(self._lib.pas_model_write_intermediate(self._h, name.encode(), a.ctypes.data, a.size))
+
+    def run_phase(self, phase: str, order: int = 0) -> None:
+        _check(self._lib.pas_model_run_phase(self._h, PHASES[phase], order))
+
+    def last_timings(self) -> Dict[str, float]:
+        n = ctypes.c_int(0)
+        _check(self._lib.pas_model_last_timings(self._h, ctypes.byref(n), None, None))
+        names = (ctypes.c_char_p * n.value)()
+        ms = (ctypes.c_float * n.value)()
+        _check(self._lib.pas_model_last_timings(self._h, ctypes.byref(n), names, ms))
+        out: Dict[str, float] = {}
+        for k, v in zip(names, ms):
+            key = k.decode()
+            out[key] = out.get(key, 0.0) + float(v)
+        return out
+
+    def last_launch_count(self) -> int:
+        n = ctypes.c_int()
+        _check(self._lib.pas_model_last_launch_count(self._h, ctypes.byref(n)))
+        return n.value
+
+    def attach_world(self, rank: int, world_size: int, unique_id: Optional[bytes]) -> None:
+        _check(self._lib.pas_model_attach_world(self._h, rank, world_size, unique_id))
