@@ -159,6 +159,12 @@ pas_status pas_model_channels(const pas_model* model, int* num_channels, double*
  * (atmosphere/model.cc:909, 925-943). */
 pas_status pas_model_luminance_matrix(const pas_model* model, float* out);
 
+/* The same two without a model (and without a GPU): the wavelength grid and the luminance matrices
+ * Model::Init derives from num_precomputed_wavelengths (atmosphere/model.cc:907-943). lambdas and
+ * luminance_from_radiance may be NULL to query *num_channels only. */
+pas_status pas_spectral_channels(unsigned int num_precomputed_wavelengths, int* num_channels,
+                                 double* lambdas, float* luminance_from_radiance);
+
 /* When enabled, Init keeps a device copy of every intermediate (planar per channel, texel order
  * x fastest): "transmittance", "delta_irradiance_<n>", "delta_rayleigh", "delta_mie",
  * "delta_density_<n>", "delta_multiple_<n>". Costs memory and time; off by default. */
@@ -184,6 +190,12 @@ pas_status pas_model_last_timings(const pas_model* model, int* count, const char
 /* Kernels launched by the last pas_model_init. */
 pas_status pas_model_last_launch_count(const pas_model* model, int* launches);
 
+/* Roofline denominators of this path, measured on the device with saturating microbenchmarks (CUDA
+ * events): dense FP32 FMA throughput in TFLOP/s and MUFU (SFU) throughput in Gop/s. Used by bench.py;
+ * the driver's MEASURED_PEAKS.json only has HBM and tensor-core figures. */
+pas_status pas_measure_device_peaks(int device, double* fp32_tflops, double* mufu_gops,
+                                    int* sm_count);
+
 /* ---- multi-GPU (one process per GPU; no reference counterpart) ------------------------------ */
 
 #define PAS_NCCL_UNIQUE_ID_BYTES 128
@@ -195,6 +207,14 @@ pas_status pas_nccl_unique_id(void* id_bytes);
  * pas_model_init. After Init every rank holds the complete final tables. */
 pas_status pas_model_attach_world(pas_model* model, int rank, int world_size,
                                   const void* nccl_unique_id_bytes);
+/* Communicators are kept per (device, rank, world size) for the life of the process: once one
+ * exists, later models attach with nccl_unique_id_bytes == NULL. device = CUDA ordinal. */
+int pas_world_is_cached(int device, int rank, int world_size);
+
+/* Device memory of destroyed models is kept in a process-wide pool for the next pas_model_create
+ * (the demo re-creates its Model on every settings change, atmosphere/demo/demo.cc:446-494);
+ * this returns it to the driver. */
+void pas_release_cached_memory(void);
 
 const char* pas_last_error(void);
 int pas_abi_version(void);

@@ -221,6 +221,102 @@ class Oracle:
         put("irradiance", E)
         return out
 
+    # -- point functions (analytic known-answer tests, reference/functions_test.cc) ----------
+    def _call(self, name, *args, nout=0, ret=None):
+        """Calls paso_<name>(atm, *args[, out]) with doubles / ints / table pointers; returns the
+        nout-vector written by the callee, or its scalar result."""
+        f = getattr(self.l, "paso_" + name)
+        cargs = [ctypes.byref(self.atm)]
+        for a in args:
+            if a is None or isinstance(a, np.ndarray):
+                cargs.append(_p(a))
+            elif isinstance(a, (bool, int, np.integer)):
+                cargs.append(ctypes.c_int(int(a)))
+            else:
+                cargs.append(ctypes.c_double(float(a)))
+        if nout:
+            out = np.zeros(nout)
+            cargs.append(_p(out))
+            f.restype = None
+            f(*cargs)
+            return out
+        f.restype = ret or ctypes.c_double
+        return f(*cargs)
+
+    def distance_to_top(self, r, mu):
+        return self._call("distance_to_top", float(r), float(mu))
+
+    def distance_to_bottom(self, r, mu):
+        return self._call("distance_to_bottom", float(r), float(mu))
+
+    def ray_intersects_ground(self, r, mu):
+        return bool(self._call("ray_intersects_ground", float(r), float(mu), ret=ctypes.c_int))
+
+    def profile_density(self, profile, altitude):
+        return self._call("profile_density", int(profile), float(altitude))
+
+    def optical_length_to_top(self, profile, r, mu):
+        return self._call("optical_length_to_top", int(profile), float(r), float(mu))
+
+    def compute_transmittance_to_top(self, r, mu):
+        return self._call("compute_transmittance_to_top", float(r), float(mu), nout=self.nc)
+
+    def transmittance_uv_from_rmu(self, r, mu):
+        return self._call("transmittance_uv_from_rmu", float(r), float(mu), nout=2)
+
+    def rmu_from_transmittance_uv(self, u, v):
+        return self._call("rmu_from_transmittance_uv", float(u), float(v), nout=2)
+
+    def scattering_uvwz_from_rmumusnu(self, r, mu, mu_s, nu, hit):
+        return self._call("scattering_uvwz_from_rmumusnu", float(r), float(mu), float(mu_s), float(nu),
+                          bool(hit), nout=4)
+
+    def rmumusnu_from_scattering_uvwz(self, uvwz):
+        return self._call("rmumusnu_from_scattering_uvwz", np.ascontiguousarray(uvwz, dtype=np.float64),
+                          nout=5)
+
+    def rmumusnu_from_frag_coord(self, x, y, z):
+        return self._call("rmumusnu_from_frag_coord", float(x), float(y), float(z), nout=5)
+
+    def irradiance_uv_from_rmus(self, r, mu_s):
+        return self._call("irradiance_uv_from_rmus", float(r), float(mu_s), nout=2)
+
+    def rmus_from_irradiance_uv(self, u, v):
+        return self._call("rmus_from_irradiance_uv", float(u), float(v), nout=2)
+
+    def get_transmittance(self, T, r, mu, d, hit):
+        return self._call("get_transmittance", T, float(r), float(mu), float(d), bool(hit), nout=self.nc)
+
+    def get_transmittance_to_sun(self, T, r, mu_s):
+        return self._call("get_transmittance_to_sun", T, float(r), float(mu_s), nout=self.nc)
+
+    def get_scattering(self, tab, r, mu, mu_s, nu, hit):
+        return self._call("get_scattering", tab, float(r), float(mu), float(mu_s), float(nu), bool(hit), nout=self.nc)
+
+    def get_irradiance(self, E, r, mu_s):
+        return self._call("get_irradiance", E, float(r), float(mu_s), nout=self.nc)
+
+    def single_scattering_point(self, T, r, mu, mu_s, nu, hit):
+        f = self.l.paso_single_scattering_point
+        ray, mie = np.zeros(self.nc), np.zeros(self.nc)
+        f.restype = None
+        f(ctypes.byref(self.atm), _p(T), *(ctypes.c_double(float(v)) for v in (r, mu, mu_s, nu)),
+          ctypes.c_int(int(bool(hit))), _p(ray), _p(mie))
+        return ray, mie
+
+    def scattering_density_point(self, T, dR, dM, dS, dE, r, mu, mu_s, nu, order):
+        return self._call("scattering_density_point", T, dR, dM, dS, dE, float(r), float(mu), float(mu_s), float(nu), int(order),
+                          nout=self.nc)
+
+    def multiple_scattering_point(self, T, dJ, r, mu, mu_s, nu, hit):
+        return self._call("multiple_scattering_point", T, dJ, float(r), float(mu), float(mu_s), float(nu), bool(hit), nout=self.nc)
+
+    def indirect_irradiance_point(self, dR, dM, dS, r, mu_s, order):
+        return self._call("indirect_irradiance_point", dR, dM, dS, float(r), float(mu_s), int(order), nout=self.nc)
+
+    def direct_irradiance_point(self, T, r, mu_s):
+        return self._call("direct_irradiance_point", T, float(r), float(mu_s), nout=self.nc)
+
 
 def rayleigh_phase(nu):
     """atmosphere/functions.glsl:739-742."""

@@ -16,6 +16,8 @@
 #include <fstream>
 #include <map>
 #include <memory>
+#include <mutex>
+#include <tuple>
 #include <sstream>
 #include <string>
 #include <utility>
@@ -126,21 +128,108 @@ void luminance_factors(const std::vector<double>& wl, const std::vector<double>&
   for (int a = 0; a < 3; ++a) k[a] *= pas::kMaxLuminousEfficacy;
 }
 
+// Wavelengths and luminance_from_radiance matrices of Model::Init (model.cc:907-949), all batches
+// side by side: lum is row-major [3][C].
+void spectral_channels(unsigned num_precomputed_wavelengths, std::vector<double>* lambdas,
+                       std::vector<float>* lum) {
+  if (num_precomputed_wavelengths <= 3) {
+    *lambdas = {680.0, 550.0, 440.0};
+    *lum = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    return;
+  }
+  const int iters = (int)(num_precomputed_wavelengths + 2) / 3;
+  const int C = 3 * iters;
+  const double dl = (pas::kCieLambdaMax - pas::kCieLambdaMin) / C;
+  lambdas->resize(C);
+  lum->assign(3 * (size_t)C, 0.f);
+  for (int j = 0; j < C; ++j) {
+    const double l = pas::kCieLambdaMin + (j + 0.5) * dl;
+    (*lambdas)[j] = l;
+    const double xyz[3] = {cie_value(l, 1), cie_value(l, 2), cie_value(l, 3)};
+    for (int a = 0; a < 3; ++a) {
+      // MAX_LUMINOUS_EFFICACY deliberately omitted here (model.cc:926-930)
+      (*lum)[(size_t)a * C + j] = static_cast<float>(
+          (pas::kXyzToSrgb[a][0] * xyz[0] + pas::kXyzToSrgb[a][1] * xyz[1] +
+           pas::kXyzToSrgb[a][2] * xyz[2]) * dl);
+    }
+  }
+}
+
+// Device allocations are recycled through a process-wide pool keyed by (device, size): the demo
+// re-creates its Model on every settings change (atmosphere/demo/demo.cc:446-494), and
+// cudaMalloc/cudaFree of ~0.5 GB of tables would otherwise dominate the constructor.
+struct BufferPool {
+  std::mutex mu;
+  std::multimap<std::pair<int, size_t>, void*> free_list;
+  void* take(int device, size_t bytes) {
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = free_list.find({device, bytes});
+    if (it == free_list.end()) return nullptr;
+    void* p = it->second;
+    free_list.erase(it);
+    return p;
+  }
+  void give(int device, size_t bytes, void* p) {
+    std::lock_guard<std::mutex> lock(mu);
+    free_list.insert({{device, bytes}, p});
+  }
+  void release_all() {
+    std::lock_guard<std::mutex> lock(mu);
+    int current = 0;
+    cudaGetDevice(&current);
+    for (auto& kv : free_list) {
+      cudaSetDevice(kv.first.first);
+      cudaFree(kv.second);
+    }
+    free_list.clear();
+    cudaSetDevice(current);
+  }
+};
+BufferPool& pool() {
+  static BufferPool* p = new BufferPool();  // intentionally leaked: outlives the CUDA context teardown
+  return *p;
+}
+
 struct DeviceBuffer {
   void* p = nullptr;
   size_t bytes = 0;
-  ~DeviceBuffer() { if (p) cudaFree(p); }
-  cudaError_t ensure(size_t n) {
-    if (n <= bytes) return cudaSuccess;
-    if (p) cudaFree(p);
+  int device = 0;
+  ~DeviceBuffer() { release(); }
+  void release() {
+    if (p) pool().give(device, bytes, p);
     p = nullptr;
     bytes = 0;
-    cudaError_t e = cudaMalloc(&p, n);
-    if (e == cudaSuccess) bytes = n;
+  }
+  cudaError_t ensure(size_t n) {
+    if (n <= bytes) return cudaSuccess;
+    release();
+    cudaError_t e = cudaGetDevice(&device);
+    if (e != cudaSuccess) return e;
+    p = pool().take(device, n);
+    if (p == nullptr) {
+      e = cudaMalloc(&p, n);
+      if (e != cudaSuccess) {
+        // make room and retry once
+        pool().release_all();
+        e = cudaMalloc(&p, n);
+      }
+    }
+    if (e == cudaSuccess) bytes = n; else p = nullptr;
     return e;
   }
   float* f() const { return static_cast<float*>(p); }
 };
+
+// NCCL communicators are cached per (device, rank, world size) for the life of the process, so
+// that re-creating a Model does not pay the communicator bootstrap again.
+struct CommCache {
+  std::mutex mu;
+  std::map<std::tuple<int, int, int>, ncclComm_t> comms;
+};
+CommCache& comm_cache() {
+  static CommCache* c = new CommCache();
+  return *c;
+}
 
 }  // namespace
 
@@ -544,27 +633,7 @@ pas_status pas_model_create(const pas_model_params* p, pas_model** out) {
 
   // ---- channels and luminance matrices (model.cc:907-949) ----
   const double lam_rgb[3] = {680.0, 550.0, 440.0};
-  if (m->num_precomputed_wavelengths <= 3) {
-    m->lambdas.assign(lam_rgb, lam_rgb + 3);
-    m->lum = {1, 0, 0, 0, 1, 0, 0, 0, 1};
-  } else {
-    const int iters = (int)(m->num_precomputed_wavelengths + 2) / 3;
-    const int C = 3 * iters;
-    const double dl = (pas::kCieLambdaMax - pas::kCieLambdaMin) / C;
-    m->lambdas.resize(C);
-    m->lum.assign(3 * (size_t)C, 0.f);
-    for (int j = 0; j < C; ++j) {
-      const double l = pas::kCieLambdaMin + (j + 0.5) * dl;
-      m->lambdas[j] = l;
-      const double xyz[3] = {cie_value(l, 1), cie_value(l, 2), cie_value(l, 3)};
-      for (int a = 0; a < 3; ++a) {
-        // MAX_LUMINOUS_EFFICACY deliberately omitted here (model.cc:926-930)
-        m->lum[(size_t)a * C + j] = static_cast<float>(
-            (pas::kXyzToSrgb[a][0] * xyz[0] + pas::kXyzToSrgb[a][1] * xyz[1] +
-             pas::kXyzToSrgb[a][2] * xyz[2]) * dl);
-      }
-    }
-  }
+  spectral_channels(m->num_precomputed_wavelengths, &m->lambdas, &m->lum);
   const int C = m->total_channels();
   std::vector<int> sizes;
   split_channels(C, &sizes);
@@ -609,7 +678,6 @@ void pas_model_destroy(pas_model* m) {
   if (m->stream) {
     cudaStreamSynchronize(m->stream);
   }
-  if (m->comm != nullptr && nccl().ok) nccl().CommDestroy(m->comm);
   if (m->stream) cudaStreamDestroy(m->stream);
   delete m;
 }
@@ -790,6 +858,21 @@ pas_status pas_model_luminance_matrix(const pas_model* m, float* out) {
   return PAS_OK;
 }
 
+pas_status pas_spectral_channels(unsigned int num_precomputed_wavelengths, int* num_channels,
+                                 double* lambdas, float* luminance_from_radiance) {
+  if (num_channels == nullptr) return fail(PAS_ERR_INVALID_ARGUMENT, "NULL argument");
+  if (num_precomputed_wavelengths < 1 || num_precomputed_wavelengths > 240) {
+    return fail(PAS_ERR_INVALID_ARGUMENT, "num_precomputed_wavelengths must be in [1, 240]");
+  }
+  std::vector<double> lam;
+  std::vector<float> lum;
+  spectral_channels(num_precomputed_wavelengths, &lam, &lum);
+  *num_channels = (int)lam.size();
+  if (lambdas) std::copy(lam.begin(), lam.end(), lambdas);
+  if (luminance_from_radiance) std::copy(lum.begin(), lum.end(), luminance_from_radiance);
+  return PAS_OK;
+}
+
 pas_status pas_model_set_capture(pas_model* m, int enabled) {
   if (m == nullptr) return fail(PAS_ERR_INVALID_ARGUMENT, "model is NULL");
   m->capture = enabled != 0;
@@ -869,6 +952,14 @@ pas_status pas_model_last_launch_count(const pas_model* m, int* launches) {
   return PAS_OK;
 }
 
+int pas_world_is_cached(int device, int rank, int world_size) {
+  CommCache& cache = comm_cache();
+  std::lock_guard<std::mutex> lock(cache.mu);
+  return cache.comms.count(std::make_tuple(device, rank, world_size)) ? 1 : 0;
+}
+
+void pas_release_cached_memory(void) { pool().release_all(); }
+
 pas_status pas_nccl_unique_id(void* id_bytes) {
   if (id_bytes == nullptr) return fail(PAS_ERR_INVALID_ARGUMENT, "NULL argument");
   if (!nccl().ok) return fail(PAS_ERR_NCCL, "libnccl.so.2 could not be loaded");
@@ -889,15 +980,26 @@ pas_status pas_model_attach_world(pas_model* m, int rank, int world_size, const 
     m->world = 1;
     return PAS_OK;
   }
-  if (id_bytes == nullptr) return fail(PAS_ERR_INVALID_ARGUMENT, "NULL unique id");
   if (m->geom.sz.r_n % world_size != 0) {
     return fail(PAS_ERR_UNSUPPORTED, "scattering_r must be divisible by the world size");
   }
   if (!nccl().ok) return fail(PAS_ERR_NCCL, "libnccl.so.2 could not be loaded");
   PAS_CUDA(cudaSetDevice(m->device));
-  ncclUniqueId id;
-  std::memcpy(&id, id_bytes, sizeof id);
-  PAS_NCCL(nccl().CommInitRank(&m->comm, world_size, id, rank));
+  {
+    CommCache& cache = comm_cache();
+    std::lock_guard<std::mutex> lock(cache.mu);
+    const auto key = std::make_tuple(m->device, rank, world_size);
+    auto it = cache.comms.find(key);
+    if (it != cache.comms.end()) {
+      m->comm = it->second;  // communicator of an earlier model of this process
+    } else {
+      if (id_bytes == nullptr) return fail(PAS_ERR_INVALID_ARGUMENT, "NULL unique id");
+      ncclUniqueId id;
+      std::memcpy(&id, id_bytes, sizeof id);
+      PAS_NCCL(nccl().CommInitRank(&m->comm, world_size, id, rank));
+      cache.comms[key] = m->comm;
+    }
+  }
   m->rank = rank;
   m->world = world_size;
   return PAS_OK;

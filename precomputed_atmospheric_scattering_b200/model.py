@@ -89,6 +89,7 @@ def load_library() -> ctypes.CDLL:
         lib.pas_convert_spectrum_to_linear_srgb.argtypes = [ctypes.c_size_t, _DP, _DP, _DP, _DP, _DP]
         lib.pas_model_channels.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int), _DP]
         lib.pas_model_luminance_matrix.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_float)]
+        lib.pas_spectral_channels.argtypes = [ctypes.c_uint, ctypes.POINTER(ctypes.c_int), _DP, ctypes.POINTER(ctypes.c_float)]
         lib.pas_model_set_capture.argtypes = [ctypes.c_void_p, ctypes.c_int]
         lib.pas_model_read_intermediate.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_void_p, ctypes.POINTER(ctypes.c_size_t)]
         lib.pas_model_write_intermediate.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_void_p, ctypes.c_size_t]
@@ -97,6 +98,8 @@ def load_library() -> ctypes.CDLL:
         lib.pas_model_last_launch_count.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int)]
         lib.pas_nccl_unique_id.argtypes = [ctypes.c_void_p]
         lib.pas_model_attach_world.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+        lib.pas_world_is_cached.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int]
+        lib.pas_release_cached_memory.restype = None
         _lib = lib
     return _lib
 
@@ -132,6 +135,37 @@ def convert_spectrum_to_linear_srgb(wavelengths: Sequence[float], spectrum: Sequ
     _check(load_library().pas_convert_spectrum_to_linear_srgb(
         len(w), wp, sp, ctypes.byref(r), ctypes.byref(g), ctypes.byref(b)))
     return r.value, g.value, b.value
+
+
+def world_is_cached(device: int, rank: int, world_size: int) -> bool:
+    """True once this process holds an NCCL communicator for (device, rank, world_size)."""
+    return bool(load_library().pas_world_is_cached(device, rank, world_size))
+
+
+def release_cached_memory() -> None:
+    load_library().pas_release_cached_memory()
+
+
+def measure_device_peaks(device: int = 0):
+    """{'fp32_tflops', 'mufu_gops', 'sm_count'} measured on the device (FMA / MUFU microbenchmarks)."""
+    lib = load_library()
+    lib.pas_measure_device_peaks.argtypes = [ctypes.c_int, _DP, _DP, ctypes.POINTER(ctypes.c_int)]
+    f, u, n = ctypes.c_double(), ctypes.c_double(), ctypes.c_int()
+    _check(lib.pas_measure_device_peaks(device, ctypes.byref(f), ctypes.byref(u), ctypes.byref(n)))
+    return {"fp32_tflops": f.value, "mufu_gops": u.value, "sm_count": n.value}
+
+
+def spectral_channels(num_precomputed_wavelengths: int):
+    """(lambdas[C], luminance_from_radiance[3, C]) of atmosphere/model.cc:907-943; needs no GPU."""
+    lib = load_library()
+    n = ctypes.c_int()
+    _check(lib.pas_spectral_channels(int(num_precomputed_wavelengths), ctypes.byref(n), None, None))
+    lam = np.empty(n.value, dtype=np.float64)
+    lum = np.empty((3, n.value), dtype=np.float32)
+    _check(lib.pas_spectral_channels(int(num_precomputed_wavelengths), ctypes.byref(n),
+                                     lam.ctypes.data_as(_DP),
+                                     lum.ctypes.data_as(ctypes.POINTER(ctypes.c_float))))
+    return lam, lum
 
 
 class Model:
@@ -178,6 +212,7 @@ class Model:
         _check(self._lib.pas_model_create(ctypes.byref(p), ctypes.byref(self._h)))
         self.half_precision = bool(half_precision)
         self.combine_scattering_textures = bool(combine_scattering_textures)
+        self.device = device
 
     @classmethod
     def from_spec(cls, spec: AtmosphereSpec, **kw) -> "Model":

@@ -1,0 +1,78 @@
+"""Multi-GPU plumbing: one process per GPU, rendezvous through ``torch.distributed``.
+
+The compute and the NVLink exchange live in libpas_b200.so (r-slab sharding of every 3-D pass, NCCL
+all-gather of the scattering-density slabs and all-reduce of the irradiance partial sums between
+orders, see include/pas_b200.h ``pas_model_attach_world``). What is left for the host is to agree
+on an NCCL unique id and on who owns which r-layers; that is all this module does. It works with
+any torch.distributed backend (``nccl`` on the GPU box, ``gloo`` in the CPU tests).
+"""
+from __future__ import annotations
+
+from typing import Callable, List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+UNIQUE_ID_BYTES = 128  # PAS_NCCL_UNIQUE_ID_BYTES
+
+
+def slab(r_n: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous r-layers [k_begin, k_end) owned by ``rank`` (same rule as pas_model::slab in
+    csrc/pas_model.cu): layers are dealt in order, the first ``r_n % world`` ranks get one more."""
+    if not (0 <= rank < world):
+        raise ValueError("bad rank / world size")
+    base, extra = divmod(r_n, world)
+    begin = rank * base + min(rank, extra)
+    return begin, begin + base + (1 if rank < extra else 0)
+
+
+def slabs(r_n: int, world: int) -> List[Tuple[int, int]]:
+    return [slab(r_n, r, world) for r in range(world)]
+
+
+def supported_world(r_n: int, world: int) -> bool:
+    """The NCCL all-gather moves equal slabs, so the layer count must divide evenly."""
+    return world >= 1 and r_n % world == 0
+
+
+def broadcast_unique_id(make_id: Callable[[], bytes], group=None, device: Optional[torch.device] = None) -> bytes:
+    """Rank 0 creates the NCCL unique id (``nccl_unique_id`` of the C ABI), every rank returns the
+    same 128 bytes."""
+    rank = dist.get_rank(group)
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" \
+            else torch.device("cpu")
+    buf = torch.zeros(UNIQUE_ID_BYTES, dtype=torch.uint8, device=device)
+    if rank == 0:
+        raw = make_id()
+        if len(raw) != UNIQUE_ID_BYTES:
+            raise ValueError("unique id must be 128 bytes")
+        buf.copy_(torch.frombuffer(bytearray(raw), dtype=torch.uint8))
+    dist.broadcast(buf, src=0, group=group)
+    return bytes(buf.cpu().tolist())
+
+
+def attach(model, group=None) -> Tuple[int, int]:
+    """Attaches ``model`` (model.Model) to the default process group: returns (rank, world)."""
+    from .model import nccl_unique_id, world_is_cached
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    if world == 1:
+        model.attach_world(0, 1, None)
+        return rank, world
+    device = model.device if model.device is not None else torch.cuda.current_device()
+    # the library keeps one communicator per (device, rank, world) for the life of the process;
+    # every rank takes the same branch because every rank has attached the same number of models
+    uid = None if world_is_cached(device, rank, world) else broadcast_unique_id(nccl_unique_id, group)
+    model.attach_world(rank, world, uid)
+    return rank, world
+
+
+def max_over_ranks(value: float, group=None) -> float:
+    """Timing rule of the bench: the slowest rank defines the step."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return float(value)
+    device = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" \
+        else torch.device("cpu")
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    return float(t.item())

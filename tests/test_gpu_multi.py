@@ -1,0 +1,69 @@
+"""Multi-GPU parity: r-slab sharding over 2 (or more) B200s with the NCCL exchange inside the
+library must give the single-GPU tables bit for bit (same kernels, same per-texel order of
+operations; the all-gather only moves data), except the irradiance, whose per-slab partial sums are
+all-reduced (different summation order, compared at 1e-6). Skipped with fewer than 2 GPUs."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+SIZES = dict(transmittance_width=64, transmittance_height=16, scattering_r=8, scattering_mu=32,
+             scattering_mu_s=8, scattering_nu=8, irradiance_width=16, irradiance_height=4)
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world_size, port, out_dir, full_size):
+    import torch.distributed as dist
+
+    import precomputed_atmospheric_scattering_b200 as pas
+    from precomputed_atmospheric_scattering_b200 import world
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world_size,
+                            device_id=torch.device("cuda", rank))
+    try:
+        spec = pas.earth(15, half_precision=False) if full_size else pas.small_planet()
+        kw = {} if full_size else dict(sizes=SIZES)
+        for attempt in range(2):  # the second model re-uses the cached communicator
+            model = pas.Model.from_spec(spec, device=rank, **kw)
+            assert world.attach(model) == (rank, world_size)
+            model.Init(4)
+            np.savez(os.path.join(out_dir, f"rank{rank}_{attempt}.npz"), S=model.scattering,
+                     E=model.irradiance, T=model.transmittance)
+            model.close()
+        assert pas.world_is_cached(rank, rank, world_size)
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("full_size", [False, True], ids=["small", "earth15"])
+@pytest.mark.timeout(600)
+def test_two_gpus_match_one(tmp_path, pas, full_size):
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    world_size = 2
+    import torch.multiprocessing as mp
+    mp.spawn(_worker, args=(world_size, _free_port(), str(tmp_path), full_size), nprocs=world_size, join=True)
+    spec = pas.earth(15, half_precision=False) if full_size else pas.small_planet()
+    single = pas.Model.from_spec(spec, device=0, **({} if full_size else dict(sizes=SIZES)))
+    single.Init(4)
+    S, E, T = single.scattering, single.irradiance, single.transmittance
+    for rank in range(world_size):
+        for attempt in range(2):
+            got = np.load(os.path.join(tmp_path, f"rank{rank}_{attempt}.npz"))
+            assert np.array_equal(got["T"], T)
+            # orders >= 3 consume the all-reduced irradiance, whose summation order differs
+            assert np.allclose(got["S"], S, rtol=2e-6, atol=1e-7 * np.abs(S).max())
+            assert np.allclose(got["E"], E, rtol=1e-5, atol=1e-7 * np.abs(E).max())
+    single.close()

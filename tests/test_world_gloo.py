@@ -1,0 +1,75 @@
+"""world_size-2 test of the multi-GPU host logic on CPU (gloo): unique-id rendezvous, r-slab
+ownership, max-over-ranks timing, and the sharding contract itself -- the scattering-density pass
+of layer k reads only layer k of the previous order, so r-slabs computed by
+different ranks and all-gathered reproduce the single-process table. The per-slab
+compute here is the CPU oracle standing in for the kernels (checker only); the GPU version of this
+test is tests/test_gpu_multi.py."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import precomputed_atmospheric_scattering_b200 as pas
+from precomputed_atmospheric_scattering_b200 import world
+
+SIZES = dict(t_w=32, t_h=8, r=4, mu=8, mu_s=4, nu=4, e_w=8, e_h=4)
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world_size, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world_size)
+    try:
+        from oracle import oracle as orc
+        # 1. every rank ends up with rank 0's unique id
+        uid = world.broadcast_unique_id(lambda: bytes(range(128)))
+        assert uid == bytes(range(128))
+        # 2. the slowest rank defines the step time
+        assert world.max_over_ranks(10.0 + rank) == 10.0 + world_size - 1
+        # 3. r-slab sharded density pass == single-process pass, bit for bit
+        spec = pas.small_planet()
+        cp = pas.channel_params(spec, [680.0, 550.0, 440.0])
+        sz = orc.Sizes(**SIZES)
+        o = orc.Oracle(cp, sz)
+        T = o.transmittance()
+        dE = o.direct_irradiance(T)
+        dR, dM = o.single_scattering(T)
+        k0, k1 = world.slab(sz.r, rank, world_size)
+        # this rank only holds its own layers of the previous order
+        mine = lambda X: np.where((np.arange(sz.r) >= k0)[None, :, None, None] &
+                                  (np.arange(sz.r) < k1)[None, :, None, None], X, 0.0)
+        dJ = o.scattering_density(T, mine(dR), mine(dM), np.zeros_like(dR), dE, 2,
+                                  rows=(k0 * sz.mu, k1 * sz.mu))
+        part = torch.from_numpy(np.ascontiguousarray(dJ[:, k0:k1]))
+        parts = [torch.empty_like(part) for _ in range(world_size)]
+        dist.all_gather(parts, part)
+        gathered = np.concatenate([p.numpy() for p in parts], axis=1)
+        full = o.scattering_density(T, dR, dM, np.zeros_like(dR), dE, 2)
+        # the literal 4-D lookup of the oracle touches the neighbouring layer with a weight of
+        # ~1e-12; the kernels use layer k exactly
+        assert np.allclose(gathered, full, rtol=1e-9, atol=1e-300)
+        # 4. irradiance partial sums: all-reduce(sum) of per-slab contributions == full integral
+        partial = o.indirect_irradiance(mine(dR), mine(dM), np.zeros_like(dR), 1)
+        t = torch.from_numpy(partial.copy())
+        dist.all_reduce(t)
+        want = o.indirect_irradiance(dR, dM, np.zeros_like(dR), 1)
+        assert np.allclose(t.numpy(), want, rtol=1e-13, atol=1e-300)
+        open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_two_rank_world(tmp_path, orc):
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert sorted(os.listdir(tmp_path)) == ["ok0", "ok1"]
