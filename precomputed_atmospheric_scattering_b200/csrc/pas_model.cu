@@ -890,12 +890,13 @@ pas_status pas_model_read_intermediate(pas_model* m, const char* name, float* ds
   auto it = m->captured.find(name);
   float* live = nullptr;
   size_t texels = 0;
-  if (live_buffer(m, name, &live, &texels)) {
-    src = live;
-    count = texels * m->groups[0].nc;
-  } else if (it != m->captured.end()) {
+  if (it != m->captured.end()) {
+    // captured copies hold every channel of every group
     src = it->second->f();
     count = it->second->bytes / sizeof(float);
+  } else if (live_buffer(m, name, &live, &texels)) {
+    src = live;
+    count = texels * m->groups[0].nc;
   } else {
     return fail(PAS_ERR_STATE, std::string("no intermediate named '") + name + "' (capture enabled?)");
   }
