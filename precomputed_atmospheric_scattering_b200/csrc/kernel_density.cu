@@ -130,6 +130,7 @@ density_kernel(const __grid_constant__ PasGeometry g, const PasDensityDir* __res
                const float* __restrict__ tabB, const float* __restrict__ dE,
                float* __restrict__ dJ, int k_begin) {
   constexpr int NT = ORDER2 ? 2 : 1;  // tables staged
+  constexpr int CP = PAS_CHANNEL_PITCH(NC);
   extern __shared__ __align__(16) float smem_dyn[];
   __shared__ __align__(16) float sA[NT][PAS_DIR_THETA][NC][NUM];
   __shared__ float sG[PAS_DIR_THETA][NC];
@@ -141,7 +142,6 @@ density_kernel(const __grid_constant__ PasGeometry g, const PasDensityDir* __res
   const int k = k_begin + blockIdx.z;
   const int mu_n = g.sz.mu_n, nu_n = g.sz.nu_n, mu_s_n = g.sz.mu_s_n, e_w = g.sz.e_w;
   const int width = nu_n * mu_s_n;
-  const size_t plane = (size_t)width * mu_n * g.sz.r_n;
   const size_t layer = (size_t)k * mu_n * width;
   // dynamic shared memory: irradiance row 0 and its forward differences, zero padded
   const int e_pad = e_w + kNG + 1;
@@ -190,18 +190,19 @@ density_kernel(const __grid_constant__ PasGeometry g, const PasDensityDir* __res
     sE0[idx] = i < e_w ? row[i] : 0.f;
     sDE[idx] = i < e_w - 1 ? row[i + 1] - row[i] : 0.f;
   }
-  // mu-interpolated rows: value at slab s, then in place -> (V[0], D[0..NUM-2])
-  for (int idx = tid; idx < NT * PAS_DIR_THETA * NC * NUM; idx += blockDim.x) {
-    const int s = idx % NUM, c = (idx / NUM) % NC, l = (idx / (NUM * NC)) % PAS_DIR_THETA;
-    const int t = idx / (NUM * NC * PAS_DIR_THETA);
+  // mu-interpolated rows: value at slab s, then in place -> (V[0], D[0..NUM-2]). Consecutive
+  // threads read the consecutive channels of one interleaved texel (64 B at 15 channels).
+  for (int idx = tid; idx < NT * PAS_DIR_THETA * NUM * NC; idx += blockDim.x) {
+    const int c = idx % NC, s = (idx / NC) % NUM, l = (idx / (NC * NUM)) % PAS_DIR_THETA;
+    const int t = idx / (NC * NUM * PAS_DIR_THETA);
     float v = 0.f;
     if (s < nu_n) {
       const PasDensityDir d = dirs[k * PAS_DIR_THETA + l];
-      const float* tab = (t == 0 ? tabA : tabB) + (size_t)c * plane + layer + s * mu_s_n + i_mu_s;
-      const float a = tab[(size_t)d.j0 * width], b = tab[(size_t)d.j1 * width];
+      const float* tab = (t == 0 ? tabA : tabB) + (layer + s * mu_s_n + i_mu_s) * CP + c;
+      const float a = tab[(size_t)d.j0 * width * CP], b = tab[(size_t)d.j1 * width * CP];
       v = fmaf(d.w_row, b - a, a);
     }
-    (&sA[0][0][0][0])[idx] = v;
+    sA[t][l][c][s] = v;
   }
   __syncthreads();
   for (int row = tid; row < NT * PAS_DIR_THETA * NC; row += blockDim.x) {
@@ -351,9 +352,15 @@ density_kernel(const __grid_constant__ PasGeometry g, const PasDensityDir* __res
     }
   }
 
-  float* out = dJ + layer + (size_t)j * width + i_nu * mu_s_n + i_mu_s;
+  // one interleaved texel per thread: CP contiguous floats, padding channels zero
+  float4* out = reinterpret_cast<float4*>(dJ + (layer + (size_t)j * width + i_nu * mu_s_n + i_mu_s) * CP);
 #pragma unroll
-  for (int c = 0; c < NC; ++c) out[(size_t)c * plane] = acc[c];
+  for (int q = 0; q < CP / 4; ++q) {
+    float v[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) v[e] = (4 * q + e < NC) ? acc[(4 * q + e < NC) ? 4 * q + e : 0] : 0.f;
+    out[q] = make_float4(v[0], v[1], v[2], v[3]);
+  }
 }
 
 template <int NC, bool ORDER2, int NUM>

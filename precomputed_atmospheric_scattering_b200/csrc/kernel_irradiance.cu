@@ -22,6 +22,7 @@ indirect_irradiance_kernel(const __grid_constant__ PasGeometry g,
                            const float* __restrict__ tabB, float* __restrict__ dE, FinalTables fin,
                            int j_begin, int k_begin, int k_end) {
   constexpr int NT = ORDER1 ? 2 : 1;
+  constexpr int CP = PAS_CHANNEL_PITCH(NC);
   __shared__ float sV[NT][PAS_IRR_THETA][NC][PAS_MAX_NU];
   __shared__ float sRed[kThreads / 32][NC];
 
@@ -30,7 +31,6 @@ indirect_irradiance_kernel(const __grid_constant__ PasGeometry g,
   const int mu_n = g.sz.mu_n, nu_n = g.sz.nu_n, mu_s_n = g.sz.mu_s_n, r_n = g.sz.r_n;
   const int width = nu_n * mu_s_n;
   const size_t layer_stride = (size_t)width * mu_n;
-  const size_t plane = layer_stride * r_n;
 
   // texel -> (r, mu_s), functions.glsl:1539-1548
   const double r = g.bottom + unit_from_coord((j + 0.5) / g.sz.e_h, g.sz.e_h) * (g.top - g.bottom);
@@ -41,11 +41,11 @@ indirect_irradiance_kernel(const __grid_constant__ PasGeometry g,
 
   // stage: reduce (r, mu, mu_s) once per (ring, channel, slab)
   for (int idx = tid; idx < NT * PAS_IRR_THETA * NC * nu_n; idx += kThreads) {
-    const int s = idx % nu_n, c = (idx / nu_n) % NC, l = (idx / (nu_n * NC)) % PAS_IRR_THETA;
+    const int c = idx % NC, s = (idx / NC) % nu_n, l = (idx / (nu_n * NC)) % PAS_IRR_THETA;
     const int t = idx / (nu_n * NC * PAS_IRR_THETA);
     const double theta = (l + 0.5) * (kPi / (2 * PAS_IRR_THETA));
     const Tap tj = make_tap(scattering_y_from_mu(g, r, rho, cos(theta), false), mu_n);
-    const float* p = (t == 0 ? tabA : tabB) + (size_t)c * plane + s * mu_s_n;
+    const float* p = (t == 0 ? tabA : tabB) + c;  // interleaved: tab[texel * CP + c]
     float v = 0.f;
 #pragma unroll
     for (int corner = 0; corner < 8; ++corner) {
@@ -56,7 +56,7 @@ indirect_irradiance_kernel(const __grid_constant__ PasGeometry g,
                       ((corner & 1) ? ts.w : 1.f - ts.w);
       // r-slab sharding: layers owned by other ranks contribute through their partial sums
       if (kk < k_begin || kk >= k_end) continue;
-      v = fmaf(w, p[kk * layer_stride + (size_t)jj * width + ii], v);
+      v = fmaf(w, p[(kk * layer_stride + (size_t)jj * width + s * mu_s_n + ii) * CP], v);
     }
     sV[t][l][c][s] = v;
   }

@@ -45,33 +45,39 @@ transmittance_kernel(const __grid_constant__ PasGeometry g, const __grid_constan
   }
 #pragma unroll
   for (int p = 0; p < 3; ++p) acc[p] = warp_sum(acc[p]) * dx;
-  if (lane < s.nc) {
-    const double tau = s.beta_r[lane] * acc[0] + s.beta_m_ext[lane] * acc[1] +
-                       s.beta_abs[lane] * acc[2];
-    T[(size_t)lane * n + texel] = (float)exp(-tau);
+  const int cp = PAS_CHANNEL_PITCH(s.nc);
+  if (lane < cp) {
+    float t = 0.f;  // padding channels stay zero
+    if (lane < s.nc) {
+      const double tau = s.beta_r[lane] * acc[0] + s.beta_m_ext[lane] * acc[1] +
+                         s.beta_abs[lane] * acc[2];
+      t = (float)exp(-tau);
+    }
+    T[(size_t)texel * cp + lane] = t;
   }
 }
 
-__global__ void pack_rgba_kernel(const float* __restrict__ planar, int n, int nc,
+__global__ void pack_rgba_kernel(const float* __restrict__ table, int n, int nc,
                                  float* __restrict__ rgba) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n) return;
+  const int cp = PAS_CHANNEL_PITCH(nc);
   float4 v;
-  v.x = planar[t];
-  v.y = nc > 1 ? planar[(size_t)n + t] : 0.0f;
-  v.z = nc > 2 ? planar[2 * (size_t)n + t] : 0.0f;
+  v.x = table[(size_t)t * cp];
+  v.y = nc > 1 ? table[(size_t)t * cp + 1] : 0.0f;
+  v.z = nc > 2 ? table[(size_t)t * cp + 2] : 0.0f;
   v.w = 1.0f;  // unspecified in the reference (vec3 written to an RGBA target)
   reinterpret_cast<float4*>(rgba)[t] = v;
 }
 
-// Bilinear fetch of one channel plane of the transmittance table at texel-space (x, y), fp64
+// Bilinear fetch of channel c of the interleaved transmittance table at texel-space (x, y), fp64
 // arithmetic on the fp32 table (binary_function.h:103-118).
-__device__ __forceinline__ double fetch_t(const float* __restrict__ Tc, int w, const Tap& tx,
-                                          const Tap& ty) {
-  const double a = Tc[tx.i0 + w * ty.i0], b = Tc[tx.i1 + w * ty.i0];
-  const double c = Tc[tx.i0 + w * ty.i1], d = Tc[tx.i1 + w * ty.i1];
+__device__ __forceinline__ double fetch_t(const float* __restrict__ T, int cp, int c, int w,
+                                          const Tap& tx, const Tap& ty) {
+  const double a = T[(size_t)(tx.i0 + w * ty.i0) * cp + c], b = T[(size_t)(tx.i1 + w * ty.i0) * cp + c];
+  const double e = T[(size_t)(tx.i0 + w * ty.i1) * cp + c], d = T[(size_t)(tx.i1 + w * ty.i1) * cp + c];
   const double wx = tx.w, wy = ty.w;
-  return a * ((1.0 - wx) * (1.0 - wy)) + b * (wx * (1.0 - wy)) + c * ((1.0 - wx) * wy) + d * (wx * wy);
+  return a * ((1.0 - wx) * (1.0 - wy)) + b * (wx * (1.0 - wy)) + e * ((1.0 - wx) * wy) + d * (wx * wy);
 }
 
 // ComputeDirectIrradianceTexture (functions.glsl:1443-1461, 1558-1567).
@@ -91,9 +97,9 @@ __global__ void direct_irradiance_kernel(const __grid_constant__ PasGeometry g,
   double x, y;
   transmittance_xy(g, r, mu_s, &x, &y);
   const Tap tx = make_tap(x, g.sz.t_w), ty = make_tap(y, g.sz.t_h);
-  const int nt = g.sz.t_w * g.sz.t_h;
+  const int cp = PAS_CHANNEL_PITCH(s.nc);
   for (int c = 0; c < s.nc; ++c) {
-    dE[(size_t)c * n + t] = (float)(s.solar[c] * fetch_t(T + (size_t)c * nt, g.sz.t_w, tx, ty) * f);
+    dE[(size_t)c * n + t] = (float)(s.solar[c] * fetch_t(T, cp, c, g.sz.t_w, tx, ty) * f);
   }
   if (!fin.accumulate && fin.irradiance != nullptr) {
     reinterpret_cast<float4*>(fin.irradiance)[t] = make_float4(0.f, 0.f, 0.f, 1.f);
@@ -132,7 +138,7 @@ __global__ void density_setup_kernel(const __grid_constant__ PasGeometry g,
   dirs[k * PAS_DIR_THETA + l] = d;
   // transmittance to the ground along the ray, GetTransmittance(r, ct, dg, true)
   // (functions.glsl:493-519): T(r_d, -mu_d) / T(r, -mu), capped at 1.
-  const int nt = g.sz.t_w * g.sz.t_h;
+  const int cp = PAS_CHANNEL_PITCH(s.nc);
   float* Gkl = G + (size_t)(k * PAS_DIR_THETA + l) * PAS_MAX_CH;
   if (!hit) {
     for (int c = 0; c < s.nc; ++c) Gkl[c] = 0.f;
@@ -146,13 +152,40 @@ __global__ void density_setup_kernel(const __grid_constant__ PasGeometry g,
   const Tap ax = make_tap(x0, g.sz.t_w), ay = make_tap(y0, g.sz.t_h);
   const Tap bx = make_tap(x1, g.sz.t_w), by = make_tap(y1, g.sz.t_h);
   for (int c = 0; c < s.nc; ++c) {
-    const float* Tc = T + (size_t)c * nt;
-    const double t = fmin(fetch_t(Tc, g.sz.t_w, ax, ay) / fetch_t(Tc, g.sz.t_w, bx, by), 1.0);
+    const double t = fmin(fetch_t(T, cp, c, g.sz.t_w, ax, ay) / fetch_t(T, cp, c, g.sz.t_w, bx, by), 1.0);
     Gkl[c] = (float)(t * s.albedo[c] * (1.0 / kPi));
   }
 }
 
+// planar [nc][n] <-> interleaved [n][cp] (test hooks and captures present tables planar)
+__global__ void interleaved_to_planar_kernel(const float* __restrict__ src, size_t n, int nc, int cp,
+                                             float* __restrict__ dst) {
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  for (int c = 0; c < nc; ++c) dst[(size_t)c * n + t] = src[t * cp + c];
+}
+__global__ void planar_to_interleaved_kernel(const float* __restrict__ src, size_t n, int nc, int cp,
+                                             float* __restrict__ dst) {
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  for (int c = 0; c < cp; ++c) dst[t * cp + c] = c < nc ? src[(size_t)c * n + t] : 0.f;
+}
+
 }  // namespace
+
+cudaError_t launch_interleaved_to_planar(const float* src, size_t n_texels, int nc, float* dst,
+                                         cudaStream_t stream) {
+  interleaved_to_planar_kernel<<<(unsigned)((n_texels + 255) / 256), 256, 0, stream>>>(
+      src, n_texels, nc, PAS_CHANNEL_PITCH(nc), dst);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_planar_to_interleaved(const float* src, size_t n_texels, int nc, float* dst,
+                                         cudaStream_t stream) {
+  planar_to_interleaved_kernel<<<(unsigned)((n_texels + 255) / 256), 256, 0, stream>>>(
+      src, n_texels, nc, PAS_CHANNEL_PITCH(nc), dst);
+  return cudaGetLastError();
+}
 
 cudaError_t launch_transmittance(const PasGeometry& g, const PasSpectrum& s, float* T,
                                  cudaStream_t stream) {

@@ -1,7 +1,9 @@
 // Launch wrappers of the sm_100a kernels (one per pass of atmosphere/model.cc:1048-1215).
-// All tables are planar fp32 in HBM: tab[c][k][j][x] with x fastest (x = i_nu * mu_s_n + i_mu_s for
-// the 4-D tables), i.e. the reference's texel order with one plane per spectral channel. Every
-// launcher enqueues on `stream` and returns the CUDA status of the launch.
+// The multi-channel tables (T, dR, dM, dJ, dS) are channel-interleaved fp32 in HBM:
+// tab[texel * CP + c], CP = PAS_CHANNEL_PITCH(nc), texel = x + width * (j + mu_n * k) with
+// x = i_nu * mu_s_n + i_mu_s, i.e. the reference's texel order with the channels of one texel side
+// by side (pas_types.h). The irradiance tables dE are planar [c][j][i]. Every launcher enqueues on
+// `stream` and returns the CUDA status of the launch.
 #ifndef PAS_B200_CSRC_PAS_KERNELS_H_
 #define PAS_B200_CSRC_PAS_KERNELS_H_
 
@@ -25,9 +27,14 @@ struct FinalTables {
 // functions.glsl:454-463). One warp per texel, 501 samples split across lanes, fp64.
 cudaError_t launch_transmittance(const PasGeometry& g, const PasSpectrum& s, float* T,
                                  cudaStream_t stream);
-// Interleaves a 3-channel planar transmittance table into the RGBA32F product table.
-cudaError_t launch_pack_rgba(const float* planar, int n_texels, int nc, float* rgba,
+// Packs channels 0..2 of an interleaved transmittance table into the RGBA32F product table.
+cudaError_t launch_pack_rgba(const float* table, int n_texels, int nc, float* rgba,
                              cudaStream_t stream);
+// Layout conversions for the test hooks / captures, which present tables planar [c][texel].
+cudaError_t launch_interleaved_to_planar(const float* src, size_t n_texels, int nc, float* dst,
+                                         cudaStream_t stream);
+cudaError_t launch_planar_to_interleaved(const float* src, size_t n_texels, int nc, float* dst,
+                                         cudaStream_t stream);
 
 // dE[c][j][i] = direct irradiance (functions.glsl:1558-1567); zero-initialises the final E when
 // !accumulate (model.cc:139).

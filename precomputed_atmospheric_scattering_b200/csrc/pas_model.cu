@@ -371,15 +371,19 @@ struct PhaseTimer {
   }
 };
 
-// keeps a copy of an intermediate (all channels, planar) when capture is on
+// keeps a planar copy [c][texel] of an intermediate (all channels of all groups) when capture is on
 pas_status capture_copy(pas_model* m, const std::string& name, const float* src, size_t texels,
-                        int nc, int channel_offset) {
+                        int nc, int channel_offset, bool interleaved) {
   if (!m->capture) return PAS_OK;
   auto& slot = m->captured[name];
   if (!slot) slot.reset(new DeviceBuffer());
   PAS_CUDA(slot->ensure(texels * m->total_channels() * sizeof(float)));
-  PAS_CUDA(cudaMemcpyAsync(slot->f() + (size_t)channel_offset * texels, src,
-                           texels * nc * sizeof(float), cudaMemcpyDeviceToDevice, m->stream));
+  float* dst = slot->f() + (size_t)channel_offset * texels;
+  if (interleaved) {
+    PAS_CUDA(pas::launch_interleaved_to_planar(src, texels, nc, dst, m->stream));
+  } else {
+    PAS_CUDA(cudaMemcpyAsync(dst, src, texels * nc * sizeof(float), cudaMemcpyDeviceToDevice, m->stream));
+  }
   return PAS_OK;
 }
 
@@ -436,9 +440,10 @@ pas_status texture_lookup(const pas_model* m, pas_texture which, const DeviceBuf
 }
 
 // Live intermediate buffers by name (teacher-forced test hooks).
-bool live_buffer(pas_model* m, const std::string& name, float** p, size_t* texels) {
+bool live_buffer(pas_model* m, const std::string& name, float** p, size_t* texels, bool* interleaved) {
+  *interleaved = true;
   if (name == "transmittance") { *p = m->T.f(); *texels = m->n_t(); return true; }
-  if (name == "delta_irradiance") { *p = m->dE.f(); *texels = m->n_e(); return true; }
+  if (name == "delta_irradiance") { *p = m->dE.f(); *texels = m->n_e(); *interleaved = false; return true; }
   if (name == "delta_rayleigh") { *p = m->dR.f(); *texels = m->n_s(); return true; }
   if (name == "delta_mie") { *p = m->dM.f(); *texels = m->n_s(); return true; }
   if (name == "delta_density") { *p = m->dJ.f(); *texels = m->n_s(); return true; }
@@ -460,13 +465,14 @@ pas_status allocate(pas_model* m) {
   int max_nc = 0;
   for (const auto& g : m->groups) max_nc = std::max(max_nc, g.nc);
   const PasSizes& z = m->geom.sz;
-  PAS_CUDA(m->T.ensure(m->n_t() * max_nc * sizeof(float)));
-  PAS_CUDA(m->T_rgb.ensure(m->n_t() * 3 * sizeof(float)));
+  const size_t cp = PAS_CHANNEL_PITCH(max_nc);  // interleaved tables: cp floats per texel
+  PAS_CUDA(m->T.ensure(m->n_t() * cp * sizeof(float)));
+  PAS_CUDA(m->T_rgb.ensure(m->n_t() * PAS_CHANNEL_PITCH(3) * sizeof(float)));
   PAS_CUDA(m->dE.ensure(m->n_e() * max_nc * sizeof(float)));
-  PAS_CUDA(m->dR.ensure(m->n_s() * max_nc * sizeof(float)));
-  PAS_CUDA(m->dM.ensure(m->n_s() * max_nc * sizeof(float)));
-  PAS_CUDA(m->dJ.ensure(m->n_s() * max_nc * sizeof(float)));
-  PAS_CUDA(m->dS.ensure(m->n_s() * max_nc * sizeof(float)));
+  PAS_CUDA(m->dR.ensure(m->n_s() * cp * sizeof(float)));
+  PAS_CUDA(m->dM.ensure(m->n_s() * cp * sizeof(float)));
+  PAS_CUDA(m->dJ.ensure(m->n_s() * cp * sizeof(float)));
+  PAS_CUDA(m->dS.ensure(m->n_s() * cp * sizeof(float)));
   PAS_CUDA(m->dirs.ensure((size_t)z.r_n * PAS_DIR_THETA * sizeof(PasDensityDir)));
   PAS_CUDA(m->G.ensure((size_t)z.r_n * PAS_DIR_THETA * PAS_MAX_CH * sizeof(float)));
   PAS_CUDA(m->cR.ensure((size_t)z.r_n * PAS_MAX_CH * sizeof(float)));
@@ -509,19 +515,15 @@ pas_status run_phase(pas_model* m, int gi, int phase, int order, bool accumulate
       if (m->world > 1) {
         // all-gather of the density r-slabs over NVLink: every rank needs every layer its rays
         // cross in the multiple-scattering pass
-        const size_t lt = m->layer_texels();
-        PAS_NCCL(nccl().GroupStart());
-        const int base = g.sz.r_n / m->world, extra = g.sz.r_n % m->world;
-        for (int c = 0; c < sp.nc; ++c) {
-          float* plane = m->dJ.f() + (size_t)c * m->n_s();
-          if (extra == 0) {
-            PAS_NCCL(nccl().AllGather(plane + (size_t)k0 * lt, plane, (size_t)base * lt, ncclFloat,
-                                      m->comm, m->stream));
-          } else {
-            return fail(PAS_ERR_UNSUPPORTED, "scattering_r must be divisible by the world size");
-          }
+        // interleaved layout: one layer holds every channel, so each rank's slab is one
+        // contiguous run and the whole exchange is a single all-gather
+        const size_t lt = m->layer_texels() * PAS_CHANNEL_PITCH(sp.nc);
+        const int base = g.sz.r_n / m->world;
+        if (g.sz.r_n % m->world != 0) {
+          return fail(PAS_ERR_UNSUPPORTED, "scattering_r must be divisible by the world size");
         }
-        PAS_NCCL(nccl().GroupEnd());
+        PAS_NCCL(nccl().AllGather(m->dJ.f() + (size_t)k0 * lt, m->dJ.f(), (size_t)base * lt, ncclFloat,
+                                  m->comm, m->stream));
       }
       break;
     case 4: {
@@ -695,26 +697,26 @@ pas_status pas_model_init(pas_model* m, unsigned int num_scattering_orders) {
     pas_status st;
     if ((st = run_phase(m, (int)gi, 0, 0, blend)) != PAS_OK) return st;
     timer.mark("transmittance");
-    if ((st = capture_copy(m, "transmittance", m->T.f(), m->n_t(), nc, off)) != PAS_OK) return st;
+    if ((st = capture_copy(m, "transmittance", m->T.f(), m->n_t(), nc, off, true)) != PAS_OK) return st;
     if ((st = run_phase(m, (int)gi, 1, 0, blend)) != PAS_OK) return st;
     timer.mark("direct_irradiance");
-    if ((st = capture_copy(m, "delta_irradiance_1", m->dE.f(), m->n_e(), nc, off)) != PAS_OK) return st;
+    if ((st = capture_copy(m, "delta_irradiance_1", m->dE.f(), m->n_e(), nc, off, false)) != PAS_OK) return st;
     if ((st = run_phase(m, (int)gi, 2, 0, blend)) != PAS_OK) return st;
     timer.mark("single_scattering");
-    if ((st = capture_copy(m, "delta_rayleigh", m->dR.f(), m->n_s(), nc, off)) != PAS_OK) return st;
-    if ((st = capture_copy(m, "delta_mie", m->dM.f(), m->n_s(), nc, off)) != PAS_OK) return st;
+    if ((st = capture_copy(m, "delta_rayleigh", m->dR.f(), m->n_s(), nc, off, true)) != PAS_OK) return st;
+    if ((st = capture_copy(m, "delta_mie", m->dM.f(), m->n_s(), nc, off, true)) != PAS_OK) return st;
     for (unsigned order = 2; order <= num_scattering_orders; ++order) {
       const std::string tag = std::to_string(order);
       if ((st = run_phase(m, (int)gi, 3, (int)order, blend)) != PAS_OK) return st;
       timer.mark("scattering_density_" + tag);
-      if ((st = capture_copy(m, "delta_density_" + tag, m->dJ.f(), m->n_s(), nc, off)) != PAS_OK) return st;
+      if ((st = capture_copy(m, "delta_density_" + tag, m->dJ.f(), m->n_s(), nc, off, true)) != PAS_OK) return st;
       // irradiance from the radiance of the previous order (model.cc:1187-1188)
       if ((st = run_phase(m, (int)gi, 4, (int)order - 1, blend)) != PAS_OK) return st;
       timer.mark("indirect_irradiance_" + tag);
-      if ((st = capture_copy(m, "delta_irradiance_" + tag, m->dE.f(), m->n_e(), nc, off)) != PAS_OK) return st;
+      if ((st = capture_copy(m, "delta_irradiance_" + tag, m->dE.f(), m->n_e(), nc, off, false)) != PAS_OK) return st;
       if ((st = run_phase(m, (int)gi, 5, (int)order, blend)) != PAS_OK) return st;
       timer.mark("multiple_scattering_" + tag);
-      if ((st = capture_copy(m, "delta_multiple_" + tag, m->dS.f(), m->n_s(), nc, off)) != PAS_OK) return st;
+      if ((st = capture_copy(m, "delta_multiple_" + tag, m->dS.f(), m->n_s(), nc, off, true)) != PAS_OK) return st;
     }
   }
   // final transmittance at 680/550/440 nm (model.cc:951-963)
@@ -890,13 +892,15 @@ pas_status pas_model_read_intermediate(pas_model* m, const char* name, float* ds
   auto it = m->captured.find(name);
   float* live = nullptr;
   size_t texels = 0;
+  bool interleaved = false;
+  const int nc0 = m->groups[0].nc;
   if (it != m->captured.end()) {
-    // captured copies hold every channel of every group
+    // captured copies hold every channel of every group, planar
     src = it->second->f();
     count = it->second->bytes / sizeof(float);
-  } else if (live_buffer(m, name, &live, &texels)) {
+  } else if (live_buffer(m, name, &live, &texels, &interleaved)) {
     src = live;
-    count = texels * m->groups[0].nc;
+    count = texels * nc0;
   } else {
     return fail(PAS_ERR_STATE, std::string("no intermediate named '") + name + "' (capture enabled?)");
   }
@@ -905,6 +909,11 @@ pas_status pas_model_read_intermediate(pas_model* m, const char* name, float* ds
     return PAS_OK;
   }
   if (*num_floats < count) return fail(PAS_ERR_INVALID_ARGUMENT, "destination too small");
+  if (src == live && interleaved) {
+    PAS_CUDA(m->scratch.ensure(count * sizeof(float)));
+    PAS_CUDA(pas::launch_interleaved_to_planar(live, texels, nc0, m->scratch.f(), m->stream));
+    src = m->scratch.f();
+  }
   PAS_CUDA(cudaMemcpyAsync(dst, src, count * sizeof(float), cudaMemcpyDeviceToHost, m->stream));
   PAS_CUDA(cudaStreamSynchronize(m->stream));
   *num_floats = count;
@@ -917,11 +926,21 @@ pas_status pas_model_write_intermediate(pas_model* m, const char* name, const fl
   PAS_CUDA(cudaSetDevice(m->device));
   float* live = nullptr;
   size_t texels = 0;
-  if (!live_buffer(m, name, &live, &texels)) return fail(PAS_ERR_INVALID_ARGUMENT, "unknown live buffer");
-  if (num_floats != texels * m->groups[0].nc) {
-    return fail(PAS_ERR_INVALID_ARGUMENT, "expected " + std::to_string(texels * m->groups[0].nc) + " floats");
+  bool interleaved = false;
+  if (!live_buffer(m, name, &live, &texels, &interleaved)) {
+    return fail(PAS_ERR_INVALID_ARGUMENT, "unknown live buffer");
   }
-  PAS_CUDA(cudaMemcpyAsync(live, src, num_floats * sizeof(float), cudaMemcpyHostToDevice, m->stream));
+  const int nc0 = m->groups[0].nc;
+  if (num_floats != texels * nc0) {
+    return fail(PAS_ERR_INVALID_ARGUMENT, "expected " + std::to_string(texels * nc0) + " floats");
+  }
+  if (interleaved) {
+    PAS_CUDA(m->scratch.ensure(num_floats * sizeof(float)));
+    PAS_CUDA(cudaMemcpyAsync(m->scratch.f(), src, num_floats * sizeof(float), cudaMemcpyHostToDevice, m->stream));
+    PAS_CUDA(pas::launch_planar_to_interleaved(m->scratch.f(), texels, nc0, live, m->stream));
+  } else {
+    PAS_CUDA(cudaMemcpyAsync(live, src, num_floats * sizeof(float), cudaMemcpyHostToDevice, m->stream));
+  }
   PAS_CUDA(cudaStreamSynchronize(m->stream));
   return PAS_OK;
 }

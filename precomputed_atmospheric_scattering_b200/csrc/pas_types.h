@@ -16,6 +16,15 @@
 #define PAS_RAY_SAMPLES 50     // ray-march intervals (functions.glsl:707, 1297)
 #define PAS_OPTICAL_SAMPLES 500  // optical-length intervals (functions.glsl:281)
 
+// Table layout in HBM. Every multi-channel intermediate table (transmittance, delta Rayleigh / Mie,
+// scattering density, delta multiple scattering) is CHANNEL-INTERLEAVED: tab[texel * CP + c] with
+// the channel pitch CP = nc rounded up to a multiple of 4 (3 -> 4, 15 -> 16 floats = 64 B per
+// texel), texel = x + width * (j + mu_n * k) in the reference's x-fastest order. One texel is then
+// one or a few 16-byte vectors, so a table row (all channels) is a single contiguous run: the ray
+// march kernels stage rows with LDG.128 / STS.128 and the density kernel reads and writes whole
+// texels. The padding channels are kept at zero. The irradiance tables (64 x 16) stay planar.
+#define PAS_CHANNEL_PITCH(nc) (((nc) + 3) & ~3)
+
 struct PasSizes {
   int t_w, t_h;              // transmittance table: x = mu, y = r      (constants.h:47-48)
   int r_n, mu_n, mu_s_n, nu_n;  // scattering table 4-D sizes            (constants.h:50-53)
