@@ -405,14 +405,14 @@ cudaError_t launch_scattering_density(const PasGeometry& g, const PasSpectrum& s
   switch (s.nc) {
 #define PAS_CASE(N) \
   case N: return launch_nc<N>(g, dirs, G, cR, cM, dR, dM, dS, dE, order, dJ, k_begin, k_end, stream);
-    PAS_CASE(1) PAS_CASE(2) PAS_CASE(3) PAS_CASE(4) PAS_CASE(8) PAS_CASE(15) PAS_CASE(16)
+    PAS_CASE(3) PAS_CASE(4) PAS_CASE(8) PAS_CASE(15) PAS_CASE(16)
 #undef PAS_CASE
     default: return cudaErrorInvalidValue;
   }
 }
 
 bool channel_count_supported(int nc) {
-  return nc == 1 || nc == 2 || nc == 3 || nc == 4 || nc == 8 || nc == 15 || nc == 16;
+  return nc == 3 || nc == 4 || nc == 8 || nc == 15 || nc == 16;
 }
 
 }  // namespace pas

@@ -151,7 +151,7 @@ cudaError_t launch_indirect_irradiance(const PasGeometry& g, const PasSpectrum& 
   switch (s.nc) {
 #define PAS_CASE(N) \
   case N: return launch_nc<N>(g, s, dR, dM, dS, order, dE, fin, j_begin, j_end, k_begin, k_end, stream);
-    PAS_CASE(1) PAS_CASE(2) PAS_CASE(3) PAS_CASE(4) PAS_CASE(8) PAS_CASE(15) PAS_CASE(16)
+    PAS_CASE(3) PAS_CASE(4) PAS_CASE(8) PAS_CASE(15) PAS_CASE(16)
 #undef PAS_CASE
     default: return cudaErrorInvalidValue;
   }

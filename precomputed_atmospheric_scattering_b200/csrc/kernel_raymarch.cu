@@ -38,71 +38,89 @@ __device__ __forceinline__ double fetch_t(const float* __restrict__ T, int cp, i
   return a * ((1.0 - wx) * (1.0 - wy)) + b * (wx * (1.0 - wy)) + e * ((1.0 - wx) * wy) + d * (wx * wy);
 }
 
-// Shared per-sample record (written in phase A).
-struct RaySample {
-  float d;          // distance along the ray
-  float inv_r;      // 1 / r_i
-  // multiple scattering: footprint of (r_i, mu_i) in the source table, as row offsets (in texels)
-  // and the four bilinear weights
+// Shared per-sample records (written in phase A, read by every warp once per sample as three
+// 128-bit broadcast loads).
+struct __align__(16) ScatterSample {   // multiple scattering
+  // footprint of (r_i, mu_i) in the source table: row offsets (in texels) and bilinear weights
   int row00, row01, row10, row11;
   float w00, w01, w10, w11;
-  // single scattering: sun-lookup geometry at r_i
+  float d;          // distance along the ray
+  float inv_r;      // 1 / r_i
+  float pad0, pad1;
+};
+struct __align__(16) SunSample {       // single scattering: sun-lookup geometry at r_i
+  float d;          // distance along the ray
+  float inv_r;      // 1 / r_i
   float q;          // (top - r_i)(top + r_i)
   float d_min;      // top - r_i
   float x_scale;    // (t_w - 1) / (d_max - d_min)
   float cos_h;      // cosine of the horizon angle at r_i (functions.glsl:556-557)
   float inv_sun_w;  // 1 / (2 sin_h alpha_s)
+  float wy;         // weight of transmittance row y1
   float dens_r, dens_m;
   int y0, y1;       // transmittance rows bracketing r_i
-  float wy;
 };
+template <typename S>
+__device__ __forceinline__ S load_sample(const S* p) {
+  static_assert(sizeof(S) == 48, "three 16-byte vectors");
+  union { S s; float4 v[3]; } u;
+  const float4* q = reinterpret_cast<const float4*>(p);
+  u.v[0] = q[0]; u.v[1] = q[1]; u.v[2] = q[2];
+  return u.s;
+}
 
-// Phase A, one thread per sample (fp64). `want_scatter` fills the multiple-scattering fields,
-// otherwise the single-scattering ones. Tw[c] = T(r, mu, d_i)[c] * trapezoid weight * dx.
-template <int NC>
+// Phase A, one thread per sample (fp64): fills the per-sample record and
+// Tw[c] = T(r, mu, d_i)[c] * trapezoid weight * dx.
+__device__ __forceinline__ void fill_sample(const PasGeometry& g, double d, double r_i, double mu_i,
+                                            double rho_i, bool hit, ScatterSample* out) {
+  ScatterSample s;
+  const Tap tk = make_tap(rho_i / g.H * (g.sz.r_n - 1), g.sz.r_n);
+  const Tap tj = make_tap(scattering_y_from_mu(g, r_i, rho_i, mu_i, hit), g.sz.mu_n);
+  const int width = g.sz.nu_n * g.sz.mu_s_n;
+  s.row00 = (tk.i0 * g.sz.mu_n + tj.i0) * width;
+  s.row01 = (tk.i0 * g.sz.mu_n + tj.i1) * width;
+  s.row10 = (tk.i1 * g.sz.mu_n + tj.i0) * width;
+  s.row11 = (tk.i1 * g.sz.mu_n + tj.i1) * width;
+  s.w11 = tk.w * tj.w;
+  s.w10 = tk.w - s.w11;
+  s.w01 = tj.w - s.w11;
+  s.w00 = 1.0f - tk.w - tj.w + s.w11;
+  s.d = (float)d;
+  s.inv_r = (float)(1.0 / r_i);
+  s.pad0 = s.pad1 = 0.f;
+  *out = s;
+}
+__device__ __forceinline__ void fill_sample(const PasGeometry& g, double d, double r_i, double mu_i,
+                                            double rho_i, bool hit, SunSample* out) {
+  SunSample s;
+  s.d = (float)d;
+  s.inv_r = (float)(1.0 / r_i);
+  const double d_min = g.top - r_i, d_max = rho_i + g.H;
+  s.q = (float)((g.top - r_i) * (g.top + r_i));
+  s.d_min = (float)d_min;
+  s.x_scale = (float)((g.sz.t_w - 1) / (d_max - d_min));
+  const double sin_h = g.bottom / r_i;
+  s.cos_h = (float)(-sqrt(d_pos(1.0 - sin_h * sin_h)));
+  s.inv_sun_w = (float)(1.0 / (2.0 * sin_h * g.sun_angular_radius));
+  const double h = r_i - g.bottom;
+  s.dens_r = (float)profile_density(g.profiles[0], h);
+  s.dens_m = (float)profile_density(g.profiles[1], h);
+  const Tap ty = make_tap(rho_i / g.H * (g.sz.t_h - 1), g.sz.t_h);
+  s.y0 = ty.i0; s.y1 = ty.i1; s.wy = ty.w;
+  *out = s;
+}
+
+template <int NC, typename Sample>
 __device__ void ray_sample_setup(const PasGeometry& g, const float* __restrict__ T, double r,
                                  double rho, double mu, bool hit, double d_end, int i,
-                                 bool want_scatter, RaySample* out, float* Tw) {
+                                 Sample* out, float* Tw) {
   constexpr int CP = PAS_CHANNEL_PITCH(NC);
   const double dx = d_end / PAS_RAY_SAMPLES;
   const double d = i * dx;
   const double r_i = d_clamp(sqrt(d * d + 2.0 * r * mu * d + r * r), g.bottom, g.top);
   const double mu_i = d_clamp((r * mu + d) / r_i, -1.0, 1.0);
   const double rho_i = sqrt(d_pos(r_i * r_i - g.bottom * g.bottom));
-  RaySample s;
-  s.d = (float)d;
-  s.inv_r = (float)(1.0 / r_i);
-  if (want_scatter) {
-    const Tap tk = make_tap(rho_i / g.H * (g.sz.r_n - 1), g.sz.r_n);
-    const Tap tj = make_tap(scattering_y_from_mu(g, r_i, rho_i, mu_i, hit), g.sz.mu_n);
-    const int width = g.sz.nu_n * g.sz.mu_s_n;
-    s.row00 = (tk.i0 * g.sz.mu_n + tj.i0) * width;
-    s.row01 = (tk.i0 * g.sz.mu_n + tj.i1) * width;
-    s.row10 = (tk.i1 * g.sz.mu_n + tj.i0) * width;
-    s.row11 = (tk.i1 * g.sz.mu_n + tj.i1) * width;
-    s.w11 = tk.w * tj.w;
-    s.w10 = tk.w - s.w11;
-    s.w01 = tj.w - s.w11;
-    s.w00 = 1.0f - tk.w - tj.w + s.w11;
-    s.q = s.d_min = s.x_scale = s.cos_h = s.inv_sun_w = s.dens_r = s.dens_m = s.wy = 0.f;
-    s.y0 = s.y1 = 0;
-  } else {
-    s.row00 = s.row01 = s.row10 = s.row11 = 0;
-    s.w00 = s.w01 = s.w10 = s.w11 = 0.f;
-    const double d_min = g.top - r_i, d_max = rho_i + g.H;
-    s.q = (float)((g.top - r_i) * (g.top + r_i));
-    s.d_min = (float)d_min;
-    s.x_scale = (float)((g.sz.t_w - 1) / (d_max - d_min));
-    const double sin_h = g.bottom / r_i;
-    s.cos_h = (float)(-sqrt(d_pos(1.0 - sin_h * sin_h)));
-    s.inv_sun_w = (float)(1.0 / (2.0 * sin_h * g.sun_angular_radius));
-    const double h = r_i - g.bottom;
-    s.dens_r = (float)profile_density(g.profiles[0], h);
-    s.dens_m = (float)profile_density(g.profiles[1], h);
-    const Tap ty = make_tap(rho_i / g.H * (g.sz.t_h - 1), g.sz.t_h);
-    s.y0 = ty.i0; s.y1 = ty.i1; s.wy = ty.w;
-  }
-  *out = s;
+  fill_sample(g, d, r_i, mu_i, rho_i, hit, out);
   // GetTransmittance(r, mu, d, hit) (functions.glsl:493-519)
   double xa, ya, xb, yb;
   if (hit) {
@@ -159,22 +177,41 @@ __device__ __forceinline__ BlockRay block_ray(const PasGeometry& g, int k, int j
   return b;
 }
 
-// Position (in float4 units) of vector q of texel x in a staged row of Q = CP / 4 vectors per texel.
-// The XOR term spreads the same vector of 8 consecutive texels over the 8 16-byte bank groups.
+// Staged rows live in shared memory as Q = CP / 4 planes of 16-byte vectors, plane q holding vector
+// q of every texel: position (in float4 units) = q * pitch + x, pitch = W rounded up to 8, plus
+// 8 / Q. While staging, the 8 lanes of a quarter warp write 8 / Q consecutive texels x Q planes: the
+// plane padding sends them to 8 different 16-byte bank groups. While gathering, a lane reads the same
+// plane at its own texel; neighbouring lanes read neighbouring texels. With the reference's row
+// width (W = 256 = one texel per thread) pitch is a compile-time constant, so the plane offsets fold
+// into the LDS/STS immediates and the staging address is loop invariant.
 template <int Q>
-__device__ __forceinline__ int swz(int x, int q) {
-  if (Q == 1) return x;
-  constexpr int kShift = Q == 4 ? 1 : (Q == 2 ? 2 : 0);
-  return x * Q + (q ^ ((x >> kShift) & (Q - 1)));
-}
+__device__ __forceinline__ int plane_pitch(int w) { return ((w + 7) & ~7) + 8 / Q; }
+
+// Rotation of x inside its aligned group of 8 by (x >> 3): texels read with a stride of 8 (sun
+// lookups of neighbouring mu_s columns) then fall in different bank groups too.
+__device__ __forceinline__ int rot8(int x) { return (x & ~7) | ((x + (x >> 3)) & 7); }
 
 __device__ __forceinline__ float4 lerp4(float w, float4 a, float4 b) {
   return make_float4(fmaf(w, b.x - a.x, a.x), fmaf(w, b.y - a.y, a.y), fmaf(w, b.z - a.z, a.z),
                      fmaf(w, b.w - a.w, a.w));
 }
+__device__ __forceinline__ float4 combine4(float w0, float4 a, float w1, float4 b, float w2, float4 c,
+                                           float w3, float4 d) {
+  return make_float4(fmaf(w0, a.x, fmaf(w1, b.x, fmaf(w2, c.x, w3 * d.x))),
+                     fmaf(w0, a.y, fmaf(w1, b.y, fmaf(w2, c.y, w3 * d.y))),
+                     fmaf(w0, a.z, fmaf(w1, b.z, fmaf(w2, c.z, w3 * d.z))),
+                     fmaf(w0, a.w, fmaf(w1, b.w, fmaf(w2, c.w, w3 * d.w))));
+}
+__device__ __forceinline__ void fma4(float4& acc, float4 v, float4 t) {
+  acc.x = fmaf(v.x, t.x, acc.x);
+  acc.y = fmaf(v.y, t.y, acc.y);
+  acc.z = fmaf(v.z, t.z, acc.z);
+  acc.w = fmaf(v.w, t.w, acc.w);
+}
 
 // ---- multiple scattering ----------------------------------------------------------------------
-template <int NC, int MAXT, int MINB>
+// WIDTH > 0: the row width nu_n * mu_s_n is known at compile time and equals the block size.
+template <int NC, int MAXT, int MINB, int WIDTH>
 __global__ void __launch_bounds__(MAXT, MINB)
 multiple_scattering_kernel(const __grid_constant__ PasGeometry g,
                            const __grid_constant__ PasSpectrum sp, const float* __restrict__ T,
@@ -182,20 +219,21 @@ multiple_scattering_kernel(const __grid_constant__ PasGeometry g,
                            int k_begin) {
   constexpr int CP = PAS_CHANNEL_PITCH(NC), Q = CP / 4;
   extern __shared__ __align__(16) float smem_dyn[];
-  __shared__ RaySample sSample[kSamples];
+  __shared__ ScatterSample sSample[kSamples];
   __shared__ __align__(16) float sTw[kSamples][CP];
 
   const int tid = threadIdx.x;
   const int j = blockIdx.x, k = k_begin + blockIdx.y;
   const int mu_n = g.sz.mu_n, nu_n = g.sz.nu_n, mu_s_n = g.sz.mu_s_n;
-  const int width = nu_n * mu_s_n;
-  float4* sRow = reinterpret_cast<float4*>(smem_dyn);  // [2][width * Q]
+  const int width = WIDTH > 0 ? WIDTH : nu_n * mu_s_n;
+  const int nthreads = WIDTH > 0 ? WIDTH : (int)blockDim.x;
+  const int pitch = plane_pitch<Q>(width);
+  float4* sRow = reinterpret_cast<float4*>(smem_dyn);  // [2][Q * pitch]
   const float4* dJ4 = reinterpret_cast<const float4*>(dJ);
 
   const BlockRay ray = block_ray(g, k, j);
   if (tid < kSamples) {
-    ray_sample_setup<NC>(g, T, ray.r, ray.rho, ray.mu, ray.hit, ray.d_end, tid, true,
-                         &sSample[tid], sTw[tid]);
+    ray_sample_setup<NC>(g, T, ray.r, ray.rho, ray.mu, ray.hit, ray.d_end, tid, &sSample[tid], sTw[tid]);
   }
 
   // per-thread axes: mu_s (column) and nu (slab)
@@ -225,27 +263,34 @@ multiple_scattering_kernel(const __grid_constant__ PasGeometry g,
 
   if (ray.d_end > 0.0) {
     for (int i = 0; i < kSamples; ++i) {
-      const RaySample s = sSample[i];
-      float4* buf = sRow + (size_t)(i & 1) * width * Q;
+      const ScatterSample s = load_sample(&sSample[i]);
+      float4* buf = sRow + (i & 1) * Q * pitch;
       // stage: bilinear in (r, mu) applied to the whole row of texels. The row is walked as a flat
-      // array of 16-byte vectors so that a warp reads 512 contiguous bytes per load.
+      // array of 16-byte vectors so that a warp reads 512 contiguous bytes per load; all the loads
+      // of a thread are issued before the first use.
       {
         const float4* p00 = dJ4 + (size_t)s.row00 * Q;
         const float4* p01 = dJ4 + (size_t)s.row01 * Q;
         const float4* p10 = dJ4 + (size_t)s.row10 * Q;
         const float4* p11 = dJ4 + (size_t)s.row11 * Q;
         const int nvec = width * Q;
+        if (WIDTH > 0) {
+          // flat vector f = tid + it * WIDTH: plane f % Q = tid % Q, texel f / Q = tid / Q + it * (WIDTH / Q)
+          float4* dst = buf + (tid % Q) * pitch + tid / Q;
+          float4 a[Q], b[Q], c[Q], d[Q];
 #pragma unroll
-        for (int it = 0; it < Q; ++it) {
-          const int f = tid + it * (int)blockDim.x;  // blockDim.x >= width: Q rounds cover the row
-          if (f < nvec) {
-            const float4 a = __ldg(p00 + f), b = __ldg(p01 + f), c = __ldg(p10 + f), d = __ldg(p11 + f);
-            float4 v;
-            v.x = fmaf(s.w00, a.x, fmaf(s.w01, b.x, fmaf(s.w10, c.x, s.w11 * d.x)));
-            v.y = fmaf(s.w00, a.y, fmaf(s.w01, b.y, fmaf(s.w10, c.y, s.w11 * d.y)));
-            v.z = fmaf(s.w00, a.z, fmaf(s.w01, b.z, fmaf(s.w10, c.z, s.w11 * d.z)));
-            v.w = fmaf(s.w00, a.w, fmaf(s.w01, b.w, fmaf(s.w10, c.w, s.w11 * d.w)));
-            buf[swz<Q>(f / Q, f % Q)] = v;
+          for (int it = 0; it < Q; ++it) {
+            const int f = tid + it * WIDTH;
+            a[it] = __ldg(p00 + f); b[it] = __ldg(p01 + f); c[it] = __ldg(p10 + f); d[it] = __ldg(p11 + f);
+          }
+#pragma unroll
+          for (int it = 0; it < Q; ++it) {
+            dst[it * (WIDTH / Q)] = combine4(s.w00, a[it], s.w01, b[it], s.w10, c[it], s.w11, d[it]);
+          }
+        } else {
+          for (int f = tid; f < nvec; f += nthreads) {
+            buf[(f % Q) * pitch + f / Q] =
+                combine4(s.w00, __ldg(p00 + f), s.w01, __ldg(p01 + f), s.w10, __ldg(p10 + f), s.w11, __ldg(p11 + f));
           }
         }
       }
@@ -256,18 +301,17 @@ multiple_scattering_kernel(const __grid_constant__ PasGeometry g,
         const float xs = f_clamp(f_mu_s_texel_x(map, bottom * mu_s_i), 0.0f, map.scale);
         const Tap tm = make_tap_f(xs, mu_s_n);
         const float wm = tm.w;
-        const int xa0 = slab0 + tm.i0, xa1 = slab0 + tm.i1, xb0 = slab1 + tm.i0, xb1 = slab1 + tm.i1;
+        // the four corner weights of the (mu_s, nu) bilinear fetch
+        const float w11 = wnu * wm, w10 = wnu - w11, w01 = wm - w11, w00 = 1.0f - wnu - wm + w11;
+        const float4* a0 = buf + slab0 + tm.i0;
+        const float4* a1 = buf + slab0 + tm.i1;
+        const float4* b0 = buf + slab1 + tm.i0;
+        const float4* b1 = buf + slab1 + tm.i1;
         const float4* tw4 = reinterpret_cast<const float4*>(sTw[i]);
 #pragma unroll
         for (int q = 0; q < Q; ++q) {
-          const float4 va = lerp4(wm, buf[swz<Q>(xa0, q)], buf[swz<Q>(xa1, q)]);
-          const float4 vb = lerp4(wm, buf[swz<Q>(xb0, q)], buf[swz<Q>(xb1, q)]);
-          const float4 v = lerp4(wnu, va, vb);
-          const float4 t = tw4[q];
-          acc[q].x = fmaf(v.x, t.x, acc[q].x);
-          acc[q].y = fmaf(v.y, t.y, acc[q].y);
-          acc[q].z = fmaf(v.z, t.z, acc[q].z);
-          acc[q].w = fmaf(v.w, t.w, acc[q].w);
+          fma4(acc[q], combine4(w00, a0[q * pitch], w01, a1[q * pitch], w10, b0[q * pitch], w11, b1[q * pitch]),
+               tw4[q]);
         }
       }
     }
@@ -296,7 +340,8 @@ multiple_scattering_kernel(const __grid_constant__ PasGeometry g,
 }
 
 // ---- single scattering ------------------------------------------------------------------------
-template <int NC, int MAXT, int MINB>
+// WIDTH > 0: nu_n * mu_s_n == t_w == WIDTH == block size.
+template <int NC, int MAXT, int MINB, int WIDTH>
 __global__ void __launch_bounds__(MAXT, MINB)
 single_scattering_kernel(const __grid_constant__ PasGeometry g,
                          const __grid_constant__ PasSpectrum sp, const float* __restrict__ T,
@@ -304,20 +349,22 @@ single_scattering_kernel(const __grid_constant__ PasGeometry g,
                          int k_begin) {
   constexpr int CP = PAS_CHANNEL_PITCH(NC), Q = CP / 4;
   extern __shared__ __align__(16) float smem_dyn[];
-  __shared__ RaySample sSample[kSamples];
+  __shared__ SunSample sSample[kSamples];
   __shared__ __align__(16) float sTw[kSamples][CP];
 
   const int tid = threadIdx.x;
   const int j = blockIdx.x, k = k_begin + blockIdx.y;
-  const int mu_n = g.sz.mu_n, nu_n = g.sz.nu_n, mu_s_n = g.sz.mu_s_n, t_w = g.sz.t_w;
-  const int width = nu_n * mu_s_n;
-  float4* sRow = reinterpret_cast<float4*>(smem_dyn);  // [2][t_w * Q]
+  const int mu_n = g.sz.mu_n, nu_n = g.sz.nu_n, mu_s_n = g.sz.mu_s_n;
+  const int t_w = WIDTH > 0 ? WIDTH : g.sz.t_w;
+  const int width = WIDTH > 0 ? WIDTH : nu_n * mu_s_n;
+  const int nthreads = WIDTH > 0 ? WIDTH : (int)blockDim.x;
+  const int pitch = plane_pitch<Q>(t_w);
+  float4* sRow = reinterpret_cast<float4*>(smem_dyn);  // [2][Q * pitch]
   const float4* T4 = reinterpret_cast<const float4*>(T);
 
   const BlockRay ray = block_ray(g, k, j);
   if (tid < kSamples) {
-    ray_sample_setup<NC>(g, T, ray.r, ray.rho, ray.mu, ray.hit, ray.d_end, tid, false,
-                         &sSample[tid], sTw[tid]);
+    ray_sample_setup<NC>(g, T, ray.r, ray.rho, ray.mu, ray.hit, ray.d_end, tid, &sSample[tid], sTw[tid]);
   }
   const int x = tid;
   const bool active = x < width;
@@ -335,14 +382,27 @@ single_scattering_kernel(const __grid_constant__ PasGeometry g,
 
   if (ray.d_end > 0.0) {
     for (int i = 0; i < kSamples; ++i) {
-      const RaySample s = sSample[i];
-      float4* buf = sRow + (size_t)(i & 1) * t_w * Q;
+      const SunSample s = load_sample(&sSample[i]);
+      float4* buf = sRow + (i & 1) * Q * pitch;
       // stage the transmittance row at r_i (lerp of the two bracketing rows), flat 16-byte vectors
       {
         const float4* pa = T4 + (size_t)s.y0 * t_w * Q;
         const float4* pb = T4 + (size_t)s.y1 * t_w * Q;
-        for (int f = tid; f < t_w * Q; f += blockDim.x) {
-          buf[swz<Q>(f / Q, f % Q)] = lerp4(s.wy, __ldg(pa + f), __ldg(pb + f));
+        if (WIDTH > 0) {
+          float4 a[Q], b[Q];
+#pragma unroll
+          for (int it = 0; it < Q; ++it) {
+            a[it] = __ldg(pa + tid + it * WIDTH);
+            b[it] = __ldg(pb + tid + it * WIDTH);
+          }
+#pragma unroll
+          for (int it = 0; it < Q; ++it) {
+            buf[(tid % Q) * pitch + rot8(tid / Q + it * (WIDTH / Q))] = lerp4(s.wy, a[it], b[it]);
+          }
+        } else {
+          for (int f = tid; f < t_w * Q; f += nthreads) {
+            buf[(f % Q) * pitch + rot8(f / Q)] = lerp4(s.wy, __ldg(pa + f), __ldg(pb + f));
+          }
         }
       }
       __syncthreads();
@@ -357,16 +417,16 @@ single_scattering_kernel(const __grid_constant__ PasGeometry g,
         const float sm = f_sat(fmaf(mu_s_i - s.cos_h, s.inv_sun_w, 0.5f));
         const float vis = sm * sm * fmaf(-2.0f, sm, 3.0f);
         const float wr = vis * s.dens_r, wm = vis * s.dens_m;
+        const float4* t0 = buf + rot8(tu.i0);
+        const float4* t1 = buf + rot8(tu.i1);
         const float4* tw4 = reinterpret_cast<const float4*>(sTw[i]);
 #pragma unroll
         for (int q = 0; q < Q; ++q) {
-          const float4 tv = lerp4(tu.w, buf[swz<Q>(tu.i0, q)], buf[swz<Q>(tu.i1, q)]);
+          const float4 tv = lerp4(tu.w, t0[q * pitch], t1[q * pitch]);
           const float4 t = tw4[q];
-          const float vx = tv.x * t.x, vy = tv.y * t.y, vz = tv.z * t.z, vw = tv.w * t.w;
-          accR[q].x = fmaf(vx, wr, accR[q].x); accM[q].x = fmaf(vx, wm, accM[q].x);
-          accR[q].y = fmaf(vy, wr, accR[q].y); accM[q].y = fmaf(vy, wm, accM[q].y);
-          accR[q].z = fmaf(vz, wr, accR[q].z); accM[q].z = fmaf(vz, wm, accM[q].z);
-          accR[q].w = fmaf(vw, wr, accR[q].w); accM[q].w = fmaf(vw, wm, accM[q].w);
+          const float4 v = make_float4(tv.x * t.x, tv.y * t.y, tv.z * t.z, tv.w * t.w);
+          fma4(accR[q], v, make_float4(wr, wr, wr, wr));
+          fma4(accM[q], v, make_float4(wm, wm, wm, wm));
         }
       }
     }
@@ -413,11 +473,6 @@ inline int round_up32(int v) { return (v + 31) / 32 * 32; }
 // Rows of up to 256 texels (the reference's 8 x 32) run with 256-thread blocks and a register
 // budget that keeps the 128-bit corner loads of a whole texel in flight; wider rows (up to 1024)
 // fall back to one big block per row.
-int tuning(const char* name, int dflt) {
-  const char* e = getenv(name);
-  return e != nullptr ? atoi(e) : dflt;
-}
-
 template <typename Kern>
 cudaError_t prepare(Kern kern, size_t dyn) {
   if (dyn > 32 * 1024) {
@@ -430,25 +485,23 @@ template <int NC>
 cudaError_t launch_multiple_nc(const PasGeometry& g, const PasSpectrum& s, const float* T,
                                const float* dJ, float* dS, FinalTables fin, int k_begin, int k_end,
                                cudaStream_t stream) {
-  constexpr int CP = PAS_CHANNEL_PITCH(NC);
+  constexpr int CP = PAS_CHANNEL_PITCH(NC), Q = CP / 4;
   const int width = g.sz.nu_n * g.sz.mu_s_n;
   if (width > 1024) return cudaErrorInvalidValue;
   const int threads = round_up32(width < kSamples ? kSamples : width);
-  const size_t dyn = (size_t)2 * CP * width * sizeof(float);
+  const size_t dyn = (size_t)2 * Q * (((width + 7) & ~7) + 8 / Q) * sizeof(float4);
   const dim3 grid(g.sz.mu_n, k_end - k_begin);
   cudaError_t e;
-  if (threads <= 256) {
-    static const int blocks = tuning("PAS_MS_BLOCKS", 3);
-#define PAS_LAUNCH(B)                                                                         \
-    {                                                                                         \
-      auto kern = multiple_scattering_kernel<NC, 256, B>;                                     \
-      if ((e = prepare(kern, dyn)) != cudaSuccess) return e;                                  \
-      kern<<<grid, threads, dyn, stream>>>(g, s, T, dJ, dS, fin, k_begin);                    \
-    }
-    if (blocks == 2) PAS_LAUNCH(2) else if (blocks == 4) PAS_LAUNCH(4) else PAS_LAUNCH(3)
-#undef PAS_LAUNCH
+  if (width == 256) {
+    auto kern = multiple_scattering_kernel<NC, 256, 3, 256>;  // the reference's 8 x 32 row
+    if ((e = prepare(kern, dyn)) != cudaSuccess) return e;
+    kern<<<grid, 256, dyn, stream>>>(g, s, T, dJ, dS, fin, k_begin);
+  } else if (threads <= 256) {
+    auto kern = multiple_scattering_kernel<NC, 256, 3, 0>;
+    if ((e = prepare(kern, dyn)) != cudaSuccess) return e;
+    kern<<<grid, threads, dyn, stream>>>(g, s, T, dJ, dS, fin, k_begin);
   } else {
-    auto kern = multiple_scattering_kernel<NC, 1024, 1>;
+    auto kern = multiple_scattering_kernel<NC, 1024, 1, 0>;
     if ((e = prepare(kern, dyn)) != cudaSuccess) return e;
     kern<<<grid, threads, dyn, stream>>>(g, s, T, dJ, dS, fin, k_begin);
   }
@@ -459,25 +512,23 @@ template <int NC>
 cudaError_t launch_single_nc(const PasGeometry& g, const PasSpectrum& s, const float* T, float* dR,
                              float* dM, FinalTables fin, int k_begin, int k_end,
                              cudaStream_t stream) {
-  constexpr int CP = PAS_CHANNEL_PITCH(NC);
+  constexpr int CP = PAS_CHANNEL_PITCH(NC), Q = CP / 4;
   const int width = g.sz.nu_n * g.sz.mu_s_n;
   if (width > 1024) return cudaErrorInvalidValue;
   const int threads = round_up32(width < kSamples ? kSamples : width);
-  const size_t dyn = (size_t)2 * CP * g.sz.t_w * sizeof(float);
+  const size_t dyn = (size_t)2 * Q * (((g.sz.t_w + 7) & ~7) + 8 / Q) * sizeof(float4);
   const dim3 grid(g.sz.mu_n, k_end - k_begin);
   cudaError_t e;
-  if (threads <= 256) {
-    static const int blocks = tuning("PAS_SS_BLOCKS", 3);
-#define PAS_LAUNCH(B)                                                                         \
-    {                                                                                         \
-      auto kern = single_scattering_kernel<NC, 256, B>;                                       \
-      if ((e = prepare(kern, dyn)) != cudaSuccess) return e;                                  \
-      kern<<<grid, threads, dyn, stream>>>(g, s, T, dR, dM, fin, k_begin);                    \
-    }
-    if (blocks == 2) PAS_LAUNCH(2) else if (blocks == 4) PAS_LAUNCH(4) else PAS_LAUNCH(3)
-#undef PAS_LAUNCH
+  if (width == 256 && g.sz.t_w == 256) {
+    auto kern = single_scattering_kernel<NC, 256, 3, 256>;
+    if ((e = prepare(kern, dyn)) != cudaSuccess) return e;
+    kern<<<grid, 256, dyn, stream>>>(g, s, T, dR, dM, fin, k_begin);
+  } else if (threads <= 256) {
+    auto kern = single_scattering_kernel<NC, 256, 3, 0>;
+    if ((e = prepare(kern, dyn)) != cudaSuccess) return e;
+    kern<<<grid, threads, dyn, stream>>>(g, s, T, dR, dM, fin, k_begin);
   } else {
-    auto kern = single_scattering_kernel<NC, 1024, 1>;
+    auto kern = single_scattering_kernel<NC, 1024, 1, 0>;
     if ((e = prepare(kern, dyn)) != cudaSuccess) return e;
     kern<<<grid, threads, dyn, stream>>>(g, s, T, dR, dM, fin, k_begin);
   }
@@ -492,7 +543,7 @@ cudaError_t launch_multiple_scattering(const PasGeometry& g, const PasSpectrum& 
   switch (s.nc) {
 #define PAS_CASE(N) \
   case N: return launch_multiple_nc<N>(g, s, T, dJ, dS, fin, k_begin, k_end, stream);
-    PAS_CASE(1) PAS_CASE(2) PAS_CASE(3) PAS_CASE(4) PAS_CASE(8) PAS_CASE(15) PAS_CASE(16)
+    PAS_CASE(3) PAS_CASE(4) PAS_CASE(8) PAS_CASE(15) PAS_CASE(16)
 #undef PAS_CASE
     default: return cudaErrorInvalidValue;
   }
@@ -504,7 +555,7 @@ cudaError_t launch_single_scattering(const PasGeometry& g, const PasSpectrum& s,
   switch (s.nc) {
 #define PAS_CASE(N) \
   case N: return launch_single_nc<N>(g, s, T, dR, dM, fin, k_begin, k_end, stream);
-    PAS_CASE(1) PAS_CASE(2) PAS_CASE(3) PAS_CASE(4) PAS_CASE(8) PAS_CASE(15) PAS_CASE(16)
+    PAS_CASE(3) PAS_CASE(4) PAS_CASE(8) PAS_CASE(15) PAS_CASE(16)
 #undef PAS_CASE
     default: return cudaErrorInvalidValue;
   }

@@ -336,17 +336,21 @@ pas_status validate(const pas_model_params* p) {
   return PAS_OK;
 }
 
+// Splits the channels (always a multiple of 3, model.cc:917) into the fewest launch groups of a
+// size the kernels are instantiated for.
 void split_channels(int total, std::vector<int>* sizes) {
-  static const int kSupported[] = {16, 15, 8, 4, 3, 2, 1};
-  while (total > 0) {
+  static const int kSupported[] = {16, 15, 8, 4, 3};
+  std::vector<int> best(total + 1, 1 << 20), pick(total + 1, 0);
+  best[0] = 0;
+  for (int n = 1; n <= total; ++n) {
     for (int s : kSupported) {
-      if (s <= total && pas::channel_count_supported(s)) {
-        sizes->push_back(s);
-        total -= s;
-        break;
+      if (s <= n && pas::channel_count_supported(s) && best[n - s] + 1 < best[n]) {
+        best[n] = best[n - s] + 1;
+        pick[n] = s;
       }
     }
   }
+  for (int n = total; n > 0 && pick[n] > 0; n -= pick[n]) sizes->push_back(pick[n]);
 }
 
 struct PhaseTimer {

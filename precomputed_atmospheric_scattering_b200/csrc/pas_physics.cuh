@@ -37,11 +37,25 @@ PAS_HD float f_rsqrt(float x) {
   return 1.0f / sqrtf(x);
 #endif
 }
+// Reciprocal and square root of the fp32 inner loops go straight to the SFU (MUFU.RCP / MUFU.SQRT,
+// <= 2 ulp, no denormal fix-up branches); the arguments are table coordinates and distances whose
+// 1e-7 relative error is far below the 1e-3 parity budget.
 PAS_HD float f_rcp(float x) {
 #if defined(__CUDA_ARCH__)
-  return __frcp_rn(x);
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 #else
   return 1.0f / x;
+#endif
+}
+PAS_HD float f_sqrt(float x) {
+#if defined(__CUDA_ARCH__)
+  float y;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+#else
+  return sqrtf(x);
 #endif
 }
 PAS_HD float f_sat(float x) {
@@ -192,7 +206,7 @@ PAS_HD double mie_phase_k(double g) { return 3.0 / (8.0 * kPi) * (1.0 - g * g) /
 // Distance to the top boundary from a point given p = r*mu and q = (top - r)(top + r) >= 0,
 // rationalised so that neither sign of p cancels (functions.glsl:207-214 restated).
 PAS_HD float f_dist_top(float p, float q) {
-  float s = sqrtf(fmaf(p, p, q));
+  float s = f_sqrt(fmaf(p, p, q));
   return p > 0.0f ? q * f_rcp(p + s) : s - p;
 }
 

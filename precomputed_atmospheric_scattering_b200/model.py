@@ -15,7 +15,8 @@ import numpy as np
 from .atmospheres import AtmosphereSpec, DensityProfileLayer
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpas_b200.so")
+# PAS_B200_LIB points at an alternative build of the same library (A/B runs of kernel variants)
+LIB_PATH = os.environ.get("PAS_B200_LIB") or os.path.join(_HERE, "libpas_b200.so")
 
 TEXTURE_TRANSMITTANCE, TEXTURE_SCATTERING, TEXTURE_IRRADIANCE, TEXTURE_SINGLE_MIE = 0, 1, 2, 3
 PHASES = {"transmittance": 0, "direct_irradiance": 1, "single_scattering": 2,
