@@ -91,7 +91,7 @@ def phase_key(name: str) -> str:
 
 # ---- clocks ---------------------------------------------------------------------------------------
 class ClockSampler(threading.Thread):
-    """Samples SM clocks and throttle reasons of one GPU every 50 ms while the timed region runs."""
+    """Samples SM clocks and throttle reasons of one GPU every 5 ms while the timed region runs."""
 
     REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
                0x4: "sw_power_cap", 0x80: "hw_power_brake_slowdown"}
@@ -121,7 +121,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            self._stop_evt.wait(0.05)
+            self._stop_evt.wait(0.005)
 
     def finish(self):
         self._stop_evt.set()
@@ -308,13 +308,16 @@ def run_b200(args, rank, world_size, local_rank):
     # ---- roofline of the dominant kernel ------------------------------------------------------------
     flops, mufu, total_f, total_u = canonical_work()
     kernels = {}
+    # per-rank figures: a rank computes 1/N of every 3-D pass (its r-slab); rank 0's timings
+    share = {k: (1.0 if k == "transmittance" else 1.0 / world_size) for k in flops}
     for name, ms in phases.items():
         key = phase_key(name)
         if key in flops and ms > 0:
-            kernels[name] = {"ms": round(ms, 4), "canonical_gflop": round(flops[key] / 1e9, 2),
-                             "tflops": round(flops[key] / (ms * 1e-3) / 1e12, 2),
-                             "frac_fp32_peak": round(flops[key] / (ms * 1e-3) / 1e12 / peaks["fp32_tflops"], 4),
-                             "frac_mufu_peak": round(mufu[key] / (ms * 1e-3) / 1e9 / peaks["mufu_gops"], 4)}
+            f, u = flops[key] * share[key], mufu[key] * share[key]
+            kernels[name] = {"ms": round(ms, 4), "canonical_gflop": round(f / 1e9, 2),
+                             "tflops": round(f / (ms * 1e-3) / 1e12, 2),
+                             "frac_fp32_peak": round(f / (ms * 1e-3) / 1e12 / peaks["fp32_tflops"], 4),
+                             "frac_mufu_peak": round(u / (ms * 1e-3) / 1e9 / peaks["mufu_gops"], 4)}
     dom = max(kernels, key=lambda k: kernels[k]["ms"])
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
@@ -327,8 +330,8 @@ def run_b200(args, rank, world_size, local_rank):
                        "MEASURED_PEAKS.json has no FP32 figure",
         "mufu_peak_gops": round(peaks["mufu_gops"], 1),
         "whole_job": {"canonical_gflop": round(total_f / 1e9, 1), "canonical_mufu_gop": round(total_u / 1e9, 2),
-                      "frac_fp32_peak": round(total_f / (ms_per_step * 1e-3) / 1e12 / peaks["fp32_tflops"], 4),
-                      "frac_mufu_peak": round(total_u / (ms_per_step * 1e-3) / 1e9 / peaks["mufu_gops"], 4)},
+                      "frac_fp32_peak": round(total_f / (ms_per_step * 1e-3) / 1e12 / (world_size * peaks["fp32_tflops"]), 4),
+                      "frac_mufu_peak": round(total_u / (ms_per_step * 1e-3) / 1e9 / (world_size * peaks["mufu_gops"]), 4)},
         "kernels": kernels,
     }
     line = {
