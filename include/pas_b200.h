@@ -131,6 +131,64 @@ pas_status pas_model_read_texture(pas_model* model, pas_texture which, int as_fl
  * `directory`, raw little-endian RGBA32F (atmosphere/demo/webgl/precompute.cc:85-106). */
 pas_status pas_model_save_dat(pas_model* model, const char* directory);
 
+/* ---- render-time use of the tables --------------------------------------
+ * CUDA counterparts of the GLSL rendering API that atmosphere::Model::shader() exports
+ * (atmosphere/model.cc:221-281) and of the CPU API atmosphere::reference::Model
+ * (atmosphere/reference/model.h:62-77): GetSolarRadiance, GetSkyRadiance, GetSkyRadianceToPoint,
+ * GetSunAndSkyIrradiance and their *Luminance / *Illuminance forms. Positions are relative to the
+ * planet centre, in the model's length unit; directions are unit vectors; results are RGB at
+ * 680/550/440 nm (radiance, W/m^2/sr/nm) or linear-sRGB luminance (cd/m^2, use_luminance != 0).
+ * As in the reference (atmosphere/model.h:120-144) the radiance forms exist only for models with
+ * num_precomputed_wavelengths <= 3 (PAS_ERR_STATE otherwise). Vector arguments are arrays of n
+ * xyz triples of doubles, results arrays of n rgb triples of floats; every pointer may be a host
+ * or a device pointer (detected per pointer). pas_model_init must have run. */
+pas_status pas_model_get_solar_radiance(const pas_model* model, int use_luminance, double* rgb);
+/* functions.glsl:1705-1769. shadow_length (n doubles) and transmittance may be NULL. */
+pas_status pas_model_get_sky_radiance(pas_model* model, int use_luminance, size_t n,
+                                      const double* camera, const double* view_ray,
+                                      const double* shadow_length, const double* sun_direction,
+                                      float* radiance, float* transmittance);
+/* functions.glsl:1787-1863. */
+pas_status pas_model_get_sky_radiance_to_point(pas_model* model, int use_luminance, size_t n,
+                                               const double* camera, const double* point,
+                                               const double* shadow_length,
+                                               const double* sun_direction, float* radiance,
+                                               float* transmittance);
+/* functions.glsl:1878-1896 (model.cc:272-280 in luminance mode). */
+pas_status pas_model_get_sun_and_sky_irradiance(pas_model* model, int use_luminance, size_t n,
+                                                const double* point, const double* normal,
+                                                const double* sun_direction, float* sun_irradiance,
+                                                float* sky_irradiance);
+
+/* The uniforms of the reference's integration-test scene shader: a sphere on a spherical planet
+ * with shadows and light shafts (atmosphere/reference/model_test.glsl; uniforms
+ * reference/model_test.cc:127-134, values :310-318, 436-477). Lengths in the model's length unit. */
+typedef struct pas_scene_view {
+  double camera[3];
+  double earth_center[3];
+  double sun_direction[3];
+  double sun_size[2];          /* tan and cos of the sun's angular radius */
+  double sphere_center[3];
+  double sphere_radius;
+  double model_from_clip[9];   /* row major: view ray = M * (x, y, 1), clip x, y in [-1, 1] */
+  double ground_albedo[3];     /* at 680 / 550 / 440 nm */
+  double sphere_albedo[3];
+  double exposure;
+  int use_luminance;
+  int width, height;
+} pas_scene_view;
+
+/* Renders GetViewRayRadiance (model_test.glsl:218-348) for every pixel, pixel (0, 0) at the top left
+ * with the view rays of model_test.cc:688-711. rgb (width*height*3 floats, radiance or luminance
+ * before tone mapping) and argb (width*height words, tone-mapped with
+ * pow(1 - exp(-c * exposure), 1/2.2) and truncated like RenderCpuImage, model_test.cc:726-736) may
+ * each be NULL; host or device pointers. */
+pas_status pas_model_render_scene(pas_model* model, const pas_scene_view* view, float* rgb,
+                                  uint32_t* argb);
+/* Device time of the last render / lookup kernel in milliseconds (CUDA events on the model's
+ * stream, copies excluded). */
+pas_status pas_model_last_render_ms(const pas_model* model, float* ms);
+
 /* The GLSL source atmosphere::Model::shader() compiles (atmosphere/model.cc:691-744, 769-772):
  * header with the ATMOSPHERE constant + definitions.glsl + functions.glsl + the API wrappers.
  * definitions.glsl / functions.glsl are read from `glsl_directory` (the reference checkout's

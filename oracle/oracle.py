@@ -53,10 +53,28 @@ class _CAtm(ctypes.Structure):
                 [("profiles", ctypes.c_double * 30), ("sz", _CSizes)])
 
 
+class _CRenderTables(ctypes.Structure):
+    _fields_ = ([(n, ctypes.c_void_p) for n in
+                 ("transmittance", "scattering", "single_mie", "scattering_alpha", "irradiance")] +
+                [("sky_k", ctypes.c_double * MAX_CHANNELS), ("sun_k", ctypes.c_double * MAX_CHANNELS),
+                 ("gl_solar_radiance", ctypes.c_int)])
+
+
+class _CScene(ctypes.Structure):
+    _fields_ = [("camera", ctypes.c_double * 3), ("earth_center", ctypes.c_double * 3),
+                ("sun_direction", ctypes.c_double * 3), ("sun_size", ctypes.c_double * 2),
+                ("sphere_center", ctypes.c_double * 3), ("sphere_radius", ctypes.c_double),
+                ("model_from_clip", ctypes.c_double * 9),
+                ("ground_albedo", ctypes.c_double * MAX_CHANNELS),
+                ("sphere_albedo", ctypes.c_double * MAX_CHANNELS),
+                ("width", ctypes.c_int), ("height", ctypes.c_int)]
+
+
 def build(force: bool = False) -> str:
     """Compiles liboracle.so with the recipe in oracle/Makefile (gcc only)."""
+    srcs = [os.path.join(_HERE, f) for f in ("pas_oracle.c", "pas_oracle_render.c", "pas_oracle.h")]
     if force or not os.path.exists(LIB_PATH) or (
-            os.path.getmtime(LIB_PATH) < os.path.getmtime(os.path.join(_HERE, "pas_oracle.c"))):
+            os.path.getmtime(LIB_PATH) < max(os.path.getmtime(f) for f in srcs)):
         subprocess.check_call(["make", "-s", "-C", _HERE, LIB_PATH])
     return LIB_PATH
 
@@ -316,6 +334,86 @@ class Oracle:
 
     def direct_irradiance_point(self, T, r, mu_s):
         return self._call("direct_irradiance_point", T, float(r), float(mu_s), nout=self.nc)
+
+
+class Renderer:
+    """fp64 restatement of the render-time lookups and of the model_test.glsl scene
+    (oracle/pas_oracle_render.c) over planar float64 tables [C, ...].
+
+    `single_mie` None selects the combined-texture path: `scattering_alpha` [1, r, mu, w] then holds
+    the red single Mie channel (functions.glsl:1625-1646). sky_k / sun_k are the luminance factors
+    (1 for radiance output); gl_solar_radiance picks the GL model's solar radiance formula."""
+
+    def __init__(self, oracle: "Oracle", transmittance, scattering, irradiance, single_mie=None,
+                 scattering_alpha=None, sky_k=None, sun_k=None, gl_solar_radiance=True):
+        self.o, self.nc = oracle, oracle.nc
+        f64 = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+        self._keep = [f64(transmittance), f64(scattering), f64(single_mie), f64(scattering_alpha), f64(irradiance)]
+        assert self._keep[2] is not None or self._keep[3] is not None
+        t = _CRenderTables()
+        for name, arr in zip(("transmittance", "scattering", "single_mie", "scattering_alpha", "irradiance"),
+                             self._keep):
+            setattr(t, name, None if arr is None else arr.ctypes.data)
+        for c in range(self.nc):
+            t.sky_k[c] = 1.0 if sky_k is None else float(sky_k[c])
+            t.sun_k[c] = 1.0 if sun_k is None else float(sun_k[c])
+        t.gl_solar_radiance = int(bool(gl_solar_radiance))
+        self.tab = t
+        self.l = oracle.l
+
+    def _scene(self, view, ground_albedo=None, sphere_albedo=None) -> _CScene:
+        s = _CScene()
+        for name in ("camera", "earth_center", "sun_direction", "sun_size", "sphere_center", "model_from_clip"):
+            getattr(s, name)[:] = list(getattr(view, name))
+        s.sphere_radius = view.sphere_radius
+        ga = view.ground_albedo if ground_albedo is None else ground_albedo
+        sa = view.sphere_albedo if sphere_albedo is None else sphere_albedo
+        assert len(ga) == self.nc and len(sa) == self.nc
+        for c in range(self.nc):
+            s.ground_albedo[c], s.sphere_albedo[c] = float(ga[c]), float(sa[c])
+        s.width, s.height = view.width, view.height
+        return s
+
+    def render_scene(self, view, ground_albedo=None, sphere_albedo=None, threads: Optional[int] = None) -> np.ndarray:
+        """[H, W, C] float64 radiance (or luminance) before tone mapping."""
+        from concurrent.futures import ThreadPoolExecutor
+        s = self._scene(view, ground_albedo, sphere_albedo)
+        out = np.zeros((view.height, view.width, self.nc))
+        n = threads or os.cpu_count() or 1
+        bounds = np.linspace(0, view.height, min(n, view.height) + 1).astype(int)
+
+        def job(i):
+            return self.l.paso_render_scene(ctypes.byref(self.o.atm), ctypes.byref(self.tab), ctypes.byref(s),
+                                            _p(out), int(bounds[i]), int(bounds[i + 1]))
+        with ThreadPoolExecutor(len(bounds) - 1) as ex:
+            assert all(r == 0 for r in ex.map(job, range(len(bounds) - 1)))
+        return out
+
+    def _two(self, name, a, b, shadow_length, sun):
+        va, vb, vs = (np.array(v, dtype=np.float64) for v in (a, b, sun))
+        o0, o1 = np.zeros(self.nc), np.zeros(self.nc)
+        getattr(self.l, name)(ctypes.byref(self.o.atm), ctypes.byref(self.tab), _p(va), _p(vb),
+                              ctypes.c_double(float(shadow_length)), _p(vs), _p(o0), _p(o1))
+        return o0, o1
+
+    def sky_radiance(self, camera, view_ray, shadow_length, sun_direction):
+        return self._two("paso_sky_radiance", camera, view_ray, shadow_length, sun_direction)
+
+    def sky_radiance_to_point(self, camera, point, shadow_length, sun_direction):
+        return self._two("paso_sky_radiance_to_point", camera, point, shadow_length, sun_direction)
+
+    def sun_and_sky_irradiance(self, point, normal, sun_direction):
+        vp, vn, vs = (np.array(v, dtype=np.float64) for v in (point, normal, sun_direction))
+        o0, o1 = np.zeros(self.nc), np.zeros(self.nc)
+        self.l.paso_sun_and_sky_irradiance(ctypes.byref(self.o.atm), ctypes.byref(self.tab), _p(vp), _p(vn),
+                                           _p(vs), _p(o0), _p(o1))
+        return o0, o1
+
+    def solar_radiance(self):
+        out = np.zeros(self.nc)
+        self.l.paso_solar_radiance.restype = None
+        self.l.paso_solar_radiance(ctypes.byref(self.o.atm), ctypes.byref(self.tab), _p(out))
+        return out
 
 
 def rayleigh_phase(nu):

@@ -152,6 +152,9 @@ static void transmittance_to_top(const Atm* a, const double* T, double r, double
   paso_transmittance_uv_from_rmu(a, r, mu, uv);
   fetch2(T, a->sz.t_w, a->sz.t_h, a->nc, uv[0], uv[1], out);
 }
+void paso_get_transmittance_to_top(const Atm* a, const double* T, double r, double mu, double* out) {
+  transmittance_to_top(a, T, r, mu, out);
+}
 void paso_get_transmittance(const Atm* a, const double* T, double r, double mu, double d, int hit,
                             double* out) {
   double num[PASO_MAX_CHANNELS], den[PASO_MAX_CHANNELS];

@@ -103,6 +103,49 @@ void paso_indirect_irradiance_point(const paso_atmosphere* a, const double* dR, 
 void paso_direct_irradiance_point(const paso_atmosphere* a, const double* T, double r,
                                   double mu_s, double* out);
 
+void paso_get_transmittance_to_top(const paso_atmosphere* a, const double* T, double r, double mu,
+                                   double* out);
+
+/* ---- render-time lookups and the test scene (pas_oracle_render.c) --------------------------- */
+typedef struct paso_render_tables {
+  const double* transmittance;      /* [nc][t_h][t_w] */
+  const double* scattering;         /* [nc][r][mu][nu*mu_s]: Rayleigh + multiple scattering */
+  const double* single_mie;         /* [nc][...] or NULL = combined textures (functions.glsl:1625) */
+  const double* scattering_alpha;   /* [1][...]: red single Mie, used when single_mie == NULL */
+  const double* irradiance;         /* [nc][e_h][e_w] */
+  double sky_k[PASO_MAX_CHANNELS];  /* SKY_SPECTRAL_RADIANCE_TO_LUMINANCE, or 1 (model.cc:668-686) */
+  double sun_k[PASO_MAX_CHANNELS];  /* SUN_SPECTRAL_RADIANCE_TO_LUMINANCE, or 1 */
+  int gl_solar_radiance;            /* 1: E/(pi a^2) (model.cc:228); 0: E/(2pi(1-cos a)) (reference/model.cc:255) */
+} paso_render_tables;
+
+typedef struct paso_scene {         /* uniforms of reference/model_test.cc:127-134, 436-477 */
+  double camera[3], earth_center[3], sun_direction[3];
+  double sun_size[2];               /* tan, cos of the sun angular radius */
+  double sphere_center[3], sphere_radius;
+  double model_from_clip[9];        /* row major */
+  double ground_albedo[PASO_MAX_CHANNELS], sphere_albedo[PASO_MAX_CHANNELS];
+  int width, height;
+} paso_scene;
+
+int paso_sky_radiance(const paso_atmosphere* a, const paso_render_tables* t, const double* camera,
+                      const double* view_ray, double shadow_length, const double* sun_direction,
+                      double* radiance, double* transmittance);
+int paso_sky_radiance_to_point(const paso_atmosphere* a, const paso_render_tables* t,
+                               const double* camera, const double* point, double shadow_length,
+                               const double* sun_direction, double* radiance, double* transmittance);
+int paso_sun_and_sky_irradiance(const paso_atmosphere* a, const paso_render_tables* t,
+                                const double* point, const double* normal,
+                                const double* sun_direction, double* sun_irradiance,
+                                double* sky_irradiance);
+void paso_solar_radiance(const paso_atmosphere* a, const paso_render_tables* t, double* out);
+void paso_pixel_view_ray(const paso_scene* s, int i, int j, double* view_ray, double* view_ray_diff);
+void paso_view_ray_radiance(const paso_atmosphere* a, const paso_render_tables* t,
+                            const paso_scene* s, const double* view_ray, const double* view_ray_diff,
+                            double* radiance);
+/* out[(j * width + i) * nc + c] for rows [row_begin, row_end), j = 0 at the top. */
+int paso_render_scene(const paso_atmosphere* a, const paso_render_tables* t, const paso_scene* s,
+                      double* out, int row_begin, int row_end);
+
 #ifdef __cplusplus
 }
 #endif

@@ -35,6 +35,15 @@ def _lib():
     lib.pasref_sizes.argtypes = [ctypes.c_void_p]
     lib.pasref_uvwz_from_rmumusnu.argtypes = [ctypes.c_void_p] + [ctypes.c_double] * 4 + [ctypes.c_int, ctypes.c_void_p]
     lib.pasref_rmumusnu_from_frag_coord.argtypes = [ctypes.c_void_p] + [ctypes.c_double] * 3 + [ctypes.c_void_p]
+    lib.pasref_write.restype = ctypes.c_int
+    lib.pasref_write.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+    lib.pasref_render_scene.restype = ctypes.c_double
+    lib.pasref_render_scene.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
+                                        ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+    lib.pasref_sky_radiance.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
+                                        ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    lib.pasref_sky_radiance_to_point.argtypes = lib.pasref_sky_radiance.argtypes
+    lib.pasref_sun_and_sky_irradiance.argtypes = [ctypes.c_void_p, ctypes.c_int] + [ctypes.c_void_p] * 5
     return lib
 
 
@@ -89,6 +98,52 @@ class RefModel:
         n = self.lib.pasref_read(self.h, TABLES[table], self.n, out.ctypes.data)
         assert n == int(np.prod(shape)), (n, shape)
         return out
+
+    def write(self, table: str, array: np.ndarray) -> None:
+        """Loads [C, texels...] float64 into lanes 0..C-1 of transmittance / irradiance / delta_mie
+        (the single-Mie table of the render functions) / scattering."""
+        a = np.ascontiguousarray(array, dtype=np.float64)
+        assert a.shape[0] == self.n
+        n = self.lib.pasref_write(self.h, TABLES[table], self.n, a.ctypes.data)
+        assert n == a[0].size, (n, a.shape)
+
+    def render_scene(self, view, ground_albedo, sphere_albedo, row_stride: int = 1) -> np.ndarray:
+        """Spectral radiance [H, W, C] of the model_test.glsl scene through the reference's own
+        functions. `view` is a precomputed_atmospheric_scattering_b200.scene.SceneView; albedos
+        are per lane."""
+        scene = np.array(list(view.camera) + list(view.earth_center) + list(view.sun_direction) +
+                         list(view.sun_size) + list(view.sphere_center) + [view.sphere_radius] +
+                         list(view.model_from_clip), dtype=np.float64)
+        assert scene.size == 24
+        alb = np.ascontiguousarray(np.concatenate([ground_albedo, sphere_albedo]), dtype=np.float64)
+        assert alb.size == 2 * self.n
+        out = np.zeros((view.height, view.width, self.n), dtype=np.float64)
+        t = self.lib.pasref_render_scene(self.h, self.n, scene.ctypes.data, alb.ctypes.data, view.width,
+                                         view.height, row_stride, self.nthreads, out.ctypes.data)
+        if t < 0:
+            raise RuntimeError("pasref_render_scene failed")
+        self.last_render_seconds = t
+        return out
+
+    def _point(self, fn, a, b, shadow_length, sun):
+        va, vb, vs = (np.array(v, dtype=np.float64) for v in (a, b, sun))
+        o0, o1 = np.zeros(self.n), np.zeros(self.n)
+        fn(self.h, self.n, va.ctypes.data, vb.ctypes.data, float(shadow_length), vs.ctypes.data,
+           o0.ctypes.data, o1.ctypes.data)
+        return o0, o1
+
+    def sky_radiance(self, camera, view_ray, shadow_length, sun_direction):
+        return self._point(self.lib.pasref_sky_radiance, camera, view_ray, shadow_length, sun_direction)
+
+    def sky_radiance_to_point(self, camera, point, shadow_length, sun_direction):
+        return self._point(self.lib.pasref_sky_radiance_to_point, camera, point, shadow_length, sun_direction)
+
+    def sun_and_sky_irradiance(self, point, normal, sun_direction):
+        vp, vn, vs = (np.array(v, dtype=np.float64) for v in (point, normal, sun_direction))
+        o0, o1 = np.zeros(self.n), np.zeros(self.n)
+        self.lib.pasref_sun_and_sky_irradiance(self.h, self.n, vp.ctypes.data, vn.ctypes.data,
+                                               vs.ctypes.data, o0.ctypes.data, o1.ctypes.data)
+        return o0, o1
 
     def uvwz(self, r, mu, mu_s, nu, hit):
         out = (ctypes.c_double * 4)()

@@ -24,6 +24,7 @@
 // (external/progress_bar/util/progress_bar.cc:75). Here the thread count is a
 // parameter so that the CPU baseline can use every host core.
 
+#include <algorithm>
 #include <atomic>
 #include <chrono>
 #include <cstring>
@@ -311,6 +312,223 @@ int pasref_read(void* handle, int table, int nlanes, double* dst) {
         watt_per_square_meter_per_sr_per_nm);
     case 7: return copy3(*s->scattering, watt_per_square_meter_per_nm);
     default: return -1;
+  }
+}
+
+// Inverse of pasref_read: loads lanes 0..nlanes-1 of one table from planar
+// doubles (same layout); the remaining lanes replicate lane 0 so that they stay
+// finite. Lets the reference's render functions run on tables produced
+// elsewhere (e.g. by the CUDA path), which isolates render parity from
+// precompute parity. Returns the number of texels, or -1.
+int pasref_write(void* handle, int table, int nlanes, const double* src) {
+  State* s = static_cast<State*>(handle);
+  if (s == nullptr || nlanes < 1 || nlanes > kLanes) return -1;
+  const int W = SCATTERING_TEXTURE_WIDTH, H = SCATTERING_TEXTURE_HEIGHT;
+  auto load2 = [&](auto& tex, auto unit, int nx, int ny) {
+    for (int j = 0; j < ny; ++j) for (int i = 0; i < nx; ++i) {
+      auto v = tex.Get(i, j);
+      for (int l = 0; l < kLanes; ++l) {
+        int ls = l < nlanes ? l : 0;
+        v[l] = src[static_cast<size_t>(ls) * nx * ny + i + j * nx] * unit;
+      }
+      tex.Set(i, j, v);
+    }
+    return nx * ny;
+  };
+  auto load3 = [&](auto& tex, auto unit) {
+    for (int k = 0; k < SCATTERING_TEXTURE_DEPTH; ++k)
+      for (int j = 0; j < H; ++j) for (int i = 0; i < W; ++i) {
+        auto v = tex.Get(i, j, k);
+        size_t t = i + static_cast<size_t>(W) * (j + static_cast<size_t>(H) * k);
+        for (int l = 0; l < kLanes; ++l) {
+          int ls = l < nlanes ? l : 0;
+          v[l] = src[static_cast<size_t>(ls) * kNS + t] * unit;
+        }
+        tex.Set(i, j, k, v);
+      }
+    return kNS;
+  };
+  switch (table) {
+    case 0: return load2(*s->transmittance, Number(1.0),
+        TRANSMITTANCE_TEXTURE_WIDTH, TRANSMITTANCE_TEXTURE_HEIGHT);
+    case 2: return load2(*s->irradiance, watt_per_square_meter_per_nm,
+        IRRADIANCE_TEXTURE_WIDTH, IRRADIANCE_TEXTURE_HEIGHT);
+    case 4: return load3(*s->delta_mie, watt_per_square_meter_per_nm);
+    case 7: return load3(*s->scattering, watt_per_square_meter_per_nm);
+    default: return -1;
+  }
+}
+
+}  // extern "C"
+
+// ---- render-time functions and the test scene -------------------------------
+// The reference's own CPU renderer (atmosphere/reference/model_test.cc:632-738)
+// views atmosphere/reference/model_test.glsl as C++ inside its test fixture,
+// the "uniforms" being fields of the fixture. Same construction here: the GLSL
+// file is included where it lies, unmodified; the four model entry points call
+// the reference's GetSkyRadiance / GetSkyRadianceToPoint /
+// GetSunAndSkyIrradiance (atmosphere/reference/functions.h:223-244) on this
+// driver's tables exactly like reference::Model does
+// (atmosphere/reference/model.cc:255-283; single Mie = delta_mie).
+namespace atmosphere {
+namespace reference {
+namespace {
+
+using std::max;  // as atmosphere/reference/functions.cc:49-50 does for the GLSL text
+using std::min;
+
+struct SceneRenderer {
+  const State* state;
+  Position kSphereCenter;
+  Length kSphereRadius;
+  Position camera_;
+  Position earth_center_;
+  Direction sun_direction_;
+  dimensional::vec2 sun_size_;
+  DimensionlessSpectrum ground_albedo_;
+  DimensionlessSpectrum sphere_albedo_;
+
+  RadianceSpectrum GetSolarRadiance() {
+    // atmosphere/reference/model.cc:255-259
+    SolidAngle sun_solid_angle = 2.0 * PI *
+        (1.0 - cos(state->atmosphere.sun_angular_radius)) * sr;
+    return state->atmosphere.solar_irradiance * (1.0 / sun_solid_angle);
+  }
+  RadianceSpectrum GetSkyRadiance(Position camera, Direction view_ray,
+      Length shadow_length, Direction sun_direction,
+      DimensionlessSpectrum& transmittance) {
+    return reference::GetSkyRadiance(state->atmosphere, *state->transmittance,
+        *state->scattering, *state->delta_mie, camera, view_ray, shadow_length,
+        sun_direction, transmittance);
+  }
+  RadianceSpectrum GetSkyRadianceToPoint(Position camera, Position point,
+      Length shadow_length, Direction sun_direction,
+      DimensionlessSpectrum& transmittance) {
+    return reference::GetSkyRadianceToPoint(state->atmosphere,
+        *state->transmittance, *state->scattering, *state->delta_mie, camera,
+        point, shadow_length, sun_direction, transmittance);
+  }
+  IrradianceSpectrum GetSunAndSkyIrradiance(Position point, Direction normal,
+      Direction sun_direction, IrradianceSpectrum& sky_irradiance) {
+    return reference::GetSunAndSkyIrradiance(state->atmosphere,
+        *state->transmittance, *state->irradiance, point, normal,
+        sun_direction, sky_irradiance);
+  }
+
+#define OUT(x) x&
+#include "atmosphere/reference/model_test.glsl"
+#undef OUT
+};
+
+}  // namespace
+}  // namespace reference
+}  // namespace atmosphere
+
+extern "C" {
+
+// Renders the test scene of atmosphere/reference/model_test.glsl with the
+// reference's CPU functions on the tables currently held by `handle`
+// (transmittance, scattering, delta_mie as single Mie, irradiance).
+// scene: camera[3], earth_center[3], sun_direction[3], sun_size[2] (tan, cos),
+// sphere_center[3], sphere_radius, model_from_clip[9] (row major) = 24 doubles;
+// albedos: ground_albedo[nlanes] then sphere_albedo[nlanes].
+// out[(j*width + i)*nlanes + l] = spectral radiance of lane l at pixel (i, j),
+// j = 0 at the top, view rays as in model_test.cc:688-711.
+// Returns wall-clock seconds, or -1.
+double pasref_render_scene(void* handle, int nlanes, const double* scene,
+                           const double* albedos, int width, int height,
+                           int row_stride, int nthreads, double* out) {
+  State* s = static_cast<State*>(handle);
+  if (s == nullptr || nlanes < 1 || nlanes > kLanes || width < 1 ||
+      height < 1 || row_stride < 1) {
+    return -1.0;
+  }
+  atmosphere::reference::SceneRenderer proto;
+  proto.state = s;
+  proto.camera_ = Position(scene[0] * m, scene[1] * m, scene[2] * m);
+  proto.earth_center_ = Position(scene[3] * m, scene[4] * m, scene[5] * m);
+  proto.sun_direction_ = Direction(scene[6], scene[7], scene[8]);
+  proto.sun_size_ = dimensional::vec2(scene[9], scene[10]);
+  proto.kSphereCenter = Position(scene[11] * m, scene[12] * m, scene[13] * m);
+  proto.kSphereRadius = scene[14] * m;
+  for (int l = 0; l < kLanes; ++l) {
+    int ls = l < nlanes ? l : 0;
+    proto.ground_albedo_[l] = albedos[ls];
+    proto.sphere_albedo_[l] = albedos[nlanes + ls];
+  }
+  const double* M = scene + 15;
+  return RunRows(height, row_stride, nthreads, [&](int j) {
+    atmosphere::reference::SceneRenderer r = proto;
+    double y = 1.0 - 2.0 * (j + 0.5) / height;
+    double dy = -2.0 / height;
+    for (int i = 0; i < width; ++i) {
+      double x = 2.0 * (i + 0.5) / width - 1.0;
+      double dx = 2.0 / width;
+      Direction view_ray(M[0] * x + M[1] * y + M[2], M[3] * x + M[4] * y + M[5],
+                         M[6] * x + M[7] * y + M[8]);
+      Direction view_ray_diff(M[0] * dx + M[1] * dy, M[3] * dx + M[4] * dy,
+                              M[6] * dx + M[7] * dy);
+      RadianceSpectrum radiance = r.GetViewRayRadiance(view_ray, view_ray_diff);
+      double* o = out + (static_cast<size_t>(j) * width + i) * nlanes;
+      for (int l = 0; l < nlanes; ++l) {
+        o[l] = radiance[l].to(watt_per_square_meter_per_sr_per_nm);
+      }
+    }
+  });
+}
+
+// Point forms of the three render-time lookups. vectors are 3 doubles each.
+// (atmosphere/reference/functions.h:223-244)
+void pasref_sky_radiance(void* handle, int nlanes, const double* camera,
+                         const double* view_ray, double shadow_length,
+                         const double* sun_direction, double* radiance,
+                         double* transmittance) {
+  State* s = static_cast<State*>(handle);
+  DimensionlessSpectrum t;
+  RadianceSpectrum L = GetSkyRadiance(s->atmosphere, *s->transmittance,
+      *s->scattering, *s->delta_mie,
+      Position(camera[0] * m, camera[1] * m, camera[2] * m),
+      Direction(view_ray[0], view_ray[1], view_ray[2]), shadow_length * m,
+      Direction(sun_direction[0], sun_direction[1], sun_direction[2]), t);
+  for (int l = 0; l < nlanes; ++l) {
+    radiance[l] = L[l].to(watt_per_square_meter_per_sr_per_nm);
+    transmittance[l] = t[l]();
+  }
+}
+
+void pasref_sky_radiance_to_point(void* handle, int nlanes,
+                                  const double* camera, const double* point,
+                                  double shadow_length,
+                                  const double* sun_direction, double* radiance,
+                                  double* transmittance) {
+  State* s = static_cast<State*>(handle);
+  DimensionlessSpectrum t;
+  RadianceSpectrum L = GetSkyRadianceToPoint(s->atmosphere, *s->transmittance,
+      *s->scattering, *s->delta_mie,
+      Position(camera[0] * m, camera[1] * m, camera[2] * m),
+      Position(point[0] * m, point[1] * m, point[2] * m), shadow_length * m,
+      Direction(sun_direction[0], sun_direction[1], sun_direction[2]), t);
+  for (int l = 0; l < nlanes; ++l) {
+    radiance[l] = L[l].to(watt_per_square_meter_per_sr_per_nm);
+    transmittance[l] = t[l]();
+  }
+}
+
+void pasref_sun_and_sky_irradiance(void* handle, int nlanes,
+                                   const double* point, const double* normal,
+                                   const double* sun_direction,
+                                   double* sun_irradiance,
+                                   double* sky_irradiance) {
+  State* s = static_cast<State*>(handle);
+  IrradianceSpectrum sky;
+  IrradianceSpectrum sun = GetSunAndSkyIrradiance(s->atmosphere,
+      *s->transmittance, *s->irradiance,
+      Position(point[0] * m, point[1] * m, point[2] * m),
+      Direction(normal[0], normal[1], normal[2]),
+      Direction(sun_direction[0], sun_direction[1], sun_direction[2]), sky);
+  for (int l = 0; l < nlanes; ++l) {
+    sun_irradiance[l] = sun[l].to(watt_per_square_meter_per_nm);
+    sky_irradiance[l] = sky[l].to(watt_per_square_meter_per_nm);
   }
 }
 

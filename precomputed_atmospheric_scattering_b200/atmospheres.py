@@ -128,6 +128,17 @@ def earth(num_precomputed_wavelengths: int = 3, *, half_precision: bool = False,
         half_precision=half_precision)
 
 
+def model_test_earth(num_precomputed_wavelengths: int = 3, *, combine_scattering_textures: bool = True,
+                     half_precision: bool = True, ground_albedo: float = 0.1) -> AtmosphereSpec:
+    """The atmosphere of the reference's integration test (reference/model_test.cc:222-308): the
+    demo's Earth with a sun of angular radius 0.2678 deg and mu_s_min = cos(102 deg)."""
+    spec = earth(num_precomputed_wavelengths, half_precision=half_precision,
+                 combine_scattering_textures=combine_scattering_textures, ground_albedo=ground_albedo,
+                 sun_angular_radius=0.2678 * math.pi / 180.0)
+    spec.max_sun_zenith_angle = 102.0 * math.pi / 180.0
+    return spec
+
+
 def small_planet() -> AtmosphereSpec:
     """The synthetic planet of the reference's unit tests (reference/functions_test.cc:51-61):
     radii 1000/1500 km, Rayleigh/Mie scale heights 60/30 km. Extended here with plausible spectra so

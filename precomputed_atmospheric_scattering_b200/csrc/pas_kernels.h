@@ -77,6 +77,42 @@ cudaError_t launch_multiple_scattering(const PasGeometry& g, const PasSpectrum& 
                                        const float* dJ, float* dS, FinalTables fin, int k_begin,
                                        int k_end, cudaStream_t stream);
 
+// ---- render-time use of the tables (kernel_render.cu) -------------------------------------------
+struct RenderTables {
+  const float4* transmittance;  // RGBA32F [t_h][t_w]
+  const void* scattering;       // RGBA [r][mu][nu * mu_s], fp32 or fp16
+  const void* single_mie;       // RGBA or nullptr (combined textures: alpha of `scattering`)
+  const float4* irradiance;     // RGBA32F [e_h][e_w]
+  int half_precision;
+};
+struct RenderConstants {         // the ATMOSPHERE constants the render functions read, at 680/550/440 nm
+  double solar[3], rayleigh[3], mie_sca[3];
+  double sky_k[3], sun_k[3];     // SKY / SUN_SPECTRAL_RADIANCE_TO_LUMINANCE, or 1 (radiance mode)
+};
+struct RenderView {              // uniforms of reference/model_test.cc:127-134 + image size
+  double camera[3], earth_center[3], sun_direction[3], sun_size[2];
+  double sphere_center[3], sphere_radius;
+  double model_from_clip[9];
+  double ground_albedo[3], sphere_albedo[3];
+  double exposure;
+  int width, height;
+};
+// Test scene of reference/model_test.glsl, one thread per pixel; rgb ([h][w][3] fp32, before tone
+// mapping) and argb ([h][w] tone-mapped words, model_test.cc:726-736) may each be nullptr.
+cudaError_t launch_render_scene(const PasGeometry& g, const RenderTables& t, const RenderConstants& c,
+                                const RenderView& view, float* rgb, unsigned* argb, cudaStream_t stream);
+// GetSkyRadiance (to_point = false: target = view ray) / GetSkyRadianceToPoint (target = point) for
+// n queries; device pointers, vectors [n][3]; shadow_length and transmittance may be nullptr.
+cudaError_t launch_sky_radiance(const PasGeometry& g, const RenderTables& t, const RenderConstants& c,
+                                size_t n, bool to_point, const double* camera, const double* target,
+                                const double* shadow_length, const double* sun_direction, float* radiance,
+                                float* transmittance, cudaStream_t stream);
+// GetSunAndSkyIrradiance for n queries.
+cudaError_t launch_sun_and_sky_irradiance(const PasGeometry& g, const RenderTables& t,
+                                          const RenderConstants& c, size_t n, const double* point,
+                                          const double* normal, const double* sun_direction,
+                                          float* sun_irradiance, float* sky_irradiance, cudaStream_t stream);
+
 // Channel-group sizes the templated kernels are instantiated for.
 bool channel_count_supported(int nc);
 

@@ -253,6 +253,8 @@ struct pas_model {
   cudaStream_t stream = nullptr;
   DeviceBuffer T, dE, dR, dM, dJ, dS, dirs, G, cR, cM, T_rgb, scratch;
   DeviceBuffer S, M, E, T_rgba;
+  DeviceBuffer render_in[4], render_out[2];  // staging of host-pointer render queries
+  float last_render_ms = 0.f;
   bool initialised = false;
   bool capture = false;
   std::map<std::string, std::unique_ptr<DeviceBuffer>> captured;
@@ -1026,6 +1028,248 @@ pas_status pas_model_attach_world(pas_model* m, int rank, int world_size, const 
   }
   m->rank = rank;
   m->world = world_size;
+  return PAS_OK;
+}
+
+}  // extern "C"
+
+// ---- render-time use of the tables (kernel_render.cu) ------------------------------------------
+namespace {
+
+bool is_device_pointer(const void* p) {
+  cudaPointerAttributes attr;
+  if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged;
+}
+
+pas_status render_ready(const pas_model* m, int use_luminance) {
+  if (m == nullptr) return fail(PAS_ERR_INVALID_ARGUMENT, "model is NULL");
+  if (!m->initialised) return fail(PAS_ERR_STATE, "pas_model_init has not been called");
+  if (!use_luminance && m->num_precomputed_wavelengths > 3) {
+    // RADIANCE_API_ENABLED is only defined for <= 3 wavelengths (model.cc:771)
+    return fail(PAS_ERR_STATE, "the radiance API needs num_precomputed_wavelengths <= 3 (use luminance)");
+  }
+  return PAS_OK;
+}
+
+pas::RenderTables render_tables(const pas_model* m) {
+  pas::RenderTables t{};
+  t.transmittance = static_cast<const float4*>(m->T_rgba.p);
+  t.scattering = m->S.p;
+  t.single_mie = m->combined ? nullptr : m->M.p;
+  t.irradiance = static_cast<const float4*>(m->E.p);
+  t.half_precision = m->half ? 1 : 0;
+  return t;
+}
+
+pas::RenderConstants render_constants(const pas_model* m, int use_luminance) {
+  pas::RenderConstants c{};
+  for (int a = 0; a < 3; ++a) {
+    c.solar[a] = m->rgb_spectrum.solar[a];
+    c.rayleigh[a] = m->rgb_spectrum.beta_r[a];
+    c.mie_sca[a] = m->rgb_spectrum.beta_m_sca[a];
+    c.sky_k[a] = use_luminance ? m->sky_k[a] : 1.0;
+    c.sun_k[a] = use_luminance ? m->sun_k[a] : 1.0;
+  }
+  return c;
+}
+
+// Device view of an input array: the pointer itself if it is device memory, else a staged copy.
+pas_status stage_in(pas_model* m, int slot, const void* src, size_t bytes, const void** dev) {
+  if (src == nullptr) {
+    *dev = nullptr;
+    return PAS_OK;
+  }
+  if (is_device_pointer(src)) {
+    *dev = src;
+    return PAS_OK;
+  }
+  PAS_CUDA(m->render_in[slot].ensure(bytes));
+  PAS_CUDA(cudaMemcpyAsync(m->render_in[slot].p, src, bytes, cudaMemcpyHostToDevice, m->stream));
+  *dev = m->render_in[slot].p;
+  return PAS_OK;
+}
+pas_status stage_out(pas_model* m, int slot, void* dst, size_t bytes, void** dev) {
+  if (dst == nullptr) {
+    *dev = nullptr;
+    return PAS_OK;
+  }
+  if (is_device_pointer(dst)) {
+    *dev = dst;
+    return PAS_OK;
+  }
+  PAS_CUDA(m->render_out[slot].ensure(bytes));
+  *dev = m->render_out[slot].p;
+  return PAS_OK;
+}
+pas_status unstage_out(pas_model* m, void* dst, const void* dev, size_t bytes) {
+  if (dst != nullptr && dst != dev) {
+    PAS_CUDA(cudaMemcpyAsync(dst, dev, bytes, cudaMemcpyDeviceToHost, m->stream));
+  }
+  return PAS_OK;
+}
+
+struct RenderTimer {
+  pas_model* m;
+  cudaEvent_t a = nullptr, b = nullptr;
+  explicit RenderTimer(pas_model* model) : m(model) {
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    cudaEventRecord(a, m->stream);
+  }
+  void stop() { cudaEventRecord(b, m->stream); }
+  ~RenderTimer() {
+    if (cudaEventSynchronize(b) == cudaSuccess) cudaEventElapsedTime(&m->last_render_ms, a, b);
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+  }
+};
+
+pas_status sky_radiance_common(pas_model* m, int use_luminance, bool to_point, size_t n,
+                               const double* camera, const double* target, const double* shadow_length,
+                               const double* sun_direction, float* radiance, float* transmittance) {
+  pas_status st = render_ready(m, use_luminance);
+  if (st != PAS_OK) return st;
+  if (n == 0) return PAS_OK;
+  if (!camera || !target || !sun_direction || !radiance) return fail(PAS_ERR_INVALID_ARGUMENT, "NULL argument");
+  PAS_CUDA(cudaSetDevice(m->device));
+  const void *d_cam, *d_tgt, *d_sl, *d_sun;
+  void *d_rad, *d_tr;
+  if ((st = stage_in(m, 0, camera, n * 3 * sizeof(double), &d_cam)) != PAS_OK) return st;
+  if ((st = stage_in(m, 1, target, n * 3 * sizeof(double), &d_tgt)) != PAS_OK) return st;
+  if ((st = stage_in(m, 2, shadow_length, n * sizeof(double), &d_sl)) != PAS_OK) return st;
+  if ((st = stage_in(m, 3, sun_direction, n * 3 * sizeof(double), &d_sun)) != PAS_OK) return st;
+  if ((st = stage_out(m, 0, radiance, n * 3 * sizeof(float), &d_rad)) != PAS_OK) return st;
+  if ((st = stage_out(m, 1, transmittance, n * 3 * sizeof(float), &d_tr)) != PAS_OK) return st;
+  {
+    RenderTimer timer(m);
+    cudaError_t e = pas::launch_sky_radiance(
+        m->geom, render_tables(m), render_constants(m, use_luminance), n, to_point,
+        static_cast<const double*>(d_cam), static_cast<const double*>(d_tgt), static_cast<const double*>(d_sl),
+        static_cast<const double*>(d_sun), static_cast<float*>(d_rad), static_cast<float*>(d_tr), m->stream);
+    timer.stop();
+    PAS_CUDA(e);
+  }
+  if ((st = unstage_out(m, radiance, d_rad, n * 3 * sizeof(float))) != PAS_OK) return st;
+  if ((st = unstage_out(m, transmittance, d_tr, n * 3 * sizeof(float))) != PAS_OK) return st;
+  PAS_CUDA(cudaStreamSynchronize(m->stream));
+  return PAS_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+pas_status pas_model_get_solar_radiance(const pas_model* m, int use_luminance, double* rgb) {
+  if (m == nullptr || rgb == nullptr) return fail(PAS_ERR_INVALID_ARGUMENT, "NULL argument");
+  if (!use_luminance && m->num_precomputed_wavelengths > 3) {
+    return fail(PAS_ERR_STATE, "the radiance API needs num_precomputed_wavelengths <= 3 (use luminance)");
+  }
+  // model.cc:228-231, 254-258
+  const double a = m->sun_angular_radius;
+  for (int c = 0; c < 3; ++c) {
+    rgb[c] = m->rgb_spectrum.solar[c] / (pas::kPi * a * a) * (use_luminance ? m->sun_k[c] : 1.0);
+  }
+  return PAS_OK;
+}
+
+pas_status pas_model_get_sky_radiance(pas_model* m, int use_luminance, size_t n, const double* camera,
+                                      const double* view_ray, const double* shadow_length,
+                                      const double* sun_direction, float* radiance, float* transmittance) {
+  return sky_radiance_common(m, use_luminance, false, n, camera, view_ray, shadow_length, sun_direction,
+                             radiance, transmittance);
+}
+
+pas_status pas_model_get_sky_radiance_to_point(pas_model* m, int use_luminance, size_t n,
+                                               const double* camera, const double* point,
+                                               const double* shadow_length, const double* sun_direction,
+                                               float* radiance, float* transmittance) {
+  return sky_radiance_common(m, use_luminance, true, n, camera, point, shadow_length, sun_direction,
+                             radiance, transmittance);
+}
+
+pas_status pas_model_get_sun_and_sky_irradiance(pas_model* m, int use_luminance, size_t n,
+                                                const double* point, const double* normal,
+                                                const double* sun_direction, float* sun_irradiance,
+                                                float* sky_irradiance) {
+  pas_status st = render_ready(m, use_luminance);
+  if (st != PAS_OK) return st;
+  if (n == 0) return PAS_OK;
+  if (!point || !normal || !sun_direction || !sun_irradiance || !sky_irradiance) {
+    return fail(PAS_ERR_INVALID_ARGUMENT, "NULL argument");
+  }
+  PAS_CUDA(cudaSetDevice(m->device));
+  const void *d_p, *d_n, *d_sun;
+  void *d_e0, *d_e1;
+  if ((st = stage_in(m, 0, point, n * 3 * sizeof(double), &d_p)) != PAS_OK) return st;
+  if ((st = stage_in(m, 1, normal, n * 3 * sizeof(double), &d_n)) != PAS_OK) return st;
+  if ((st = stage_in(m, 3, sun_direction, n * 3 * sizeof(double), &d_sun)) != PAS_OK) return st;
+  if ((st = stage_out(m, 0, sun_irradiance, n * 3 * sizeof(float), &d_e0)) != PAS_OK) return st;
+  if ((st = stage_out(m, 1, sky_irradiance, n * 3 * sizeof(float), &d_e1)) != PAS_OK) return st;
+  {
+    RenderTimer timer(m);
+    cudaError_t e = pas::launch_sun_and_sky_irradiance(
+        m->geom, render_tables(m), render_constants(m, use_luminance), n, static_cast<const double*>(d_p),
+        static_cast<const double*>(d_n), static_cast<const double*>(d_sun), static_cast<float*>(d_e0),
+        static_cast<float*>(d_e1), m->stream);
+    timer.stop();
+    PAS_CUDA(e);
+  }
+  if ((st = unstage_out(m, sun_irradiance, d_e0, n * 3 * sizeof(float))) != PAS_OK) return st;
+  if ((st = unstage_out(m, sky_irradiance, d_e1, n * 3 * sizeof(float))) != PAS_OK) return st;
+  PAS_CUDA(cudaStreamSynchronize(m->stream));
+  return PAS_OK;
+}
+
+pas_status pas_model_render_scene(pas_model* m, const pas_scene_view* v, float* rgb, uint32_t* argb) {
+  if (v == nullptr) return fail(PAS_ERR_INVALID_ARGUMENT, "view is NULL");
+  pas_status st = render_ready(m, v->use_luminance);
+  if (st != PAS_OK) return st;
+  if (v->width < 1 || v->height < 1 || (size_t)v->width * v->height > ((size_t)1 << 28)) {
+    return fail(PAS_ERR_INVALID_ARGUMENT, "bad image size");
+  }
+  if (!(v->sphere_radius > 0.0) || !(v->sun_size[0] > 0.0)) {
+    return fail(PAS_ERR_INVALID_ARGUMENT, "sphere_radius and sun_size[0] must be positive");
+  }
+  if (rgb == nullptr && argb == nullptr) return fail(PAS_ERR_INVALID_ARGUMENT, "no output requested");
+  PAS_CUDA(cudaSetDevice(m->device));
+  pas::RenderView rv{};
+  std::memcpy(rv.camera, v->camera, sizeof rv.camera);
+  std::memcpy(rv.earth_center, v->earth_center, sizeof rv.earth_center);
+  std::memcpy(rv.sun_direction, v->sun_direction, sizeof rv.sun_direction);
+  std::memcpy(rv.sun_size, v->sun_size, sizeof rv.sun_size);
+  std::memcpy(rv.sphere_center, v->sphere_center, sizeof rv.sphere_center);
+  rv.sphere_radius = v->sphere_radius;
+  std::memcpy(rv.model_from_clip, v->model_from_clip, sizeof rv.model_from_clip);
+  std::memcpy(rv.ground_albedo, v->ground_albedo, sizeof rv.ground_albedo);
+  std::memcpy(rv.sphere_albedo, v->sphere_albedo, sizeof rv.sphere_albedo);
+  rv.exposure = v->exposure;
+  rv.width = v->width;
+  rv.height = v->height;
+  const size_t pixels = (size_t)v->width * v->height;
+  void *d_rgb, *d_argb;
+  if ((st = stage_out(m, 0, rgb, pixels * 3 * sizeof(float), &d_rgb)) != PAS_OK) return st;
+  if ((st = stage_out(m, 1, argb, pixels * sizeof(uint32_t), &d_argb)) != PAS_OK) return st;
+  {
+    RenderTimer timer(m);
+    cudaError_t e = pas::launch_render_scene(m->geom, render_tables(m), render_constants(m, v->use_luminance),
+                                             rv, static_cast<float*>(d_rgb), static_cast<unsigned*>(d_argb),
+                                             m->stream);
+    timer.stop();
+    PAS_CUDA(e);
+  }
+  if ((st = unstage_out(m, rgb, d_rgb, pixels * 3 * sizeof(float))) != PAS_OK) return st;
+  if ((st = unstage_out(m, argb, d_argb, pixels * sizeof(uint32_t))) != PAS_OK) return st;
+  PAS_CUDA(cudaStreamSynchronize(m->stream));
+  return PAS_OK;
+}
+
+pas_status pas_model_last_render_ms(const pas_model* m, float* ms) {
+  if (m == nullptr || ms == nullptr) return fail(PAS_ERR_INVALID_ARGUMENT, "NULL argument");
+  *ms = m->last_render_ms;
   return PAS_OK;
 }
 

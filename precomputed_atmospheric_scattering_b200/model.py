@@ -60,6 +60,16 @@ class _Params(ctypes.Structure):
         ("half_precision", ctypes.c_int), ("sizes", _Sizes), ("device", ctypes.c_int)]
 
 
+class _SceneView(ctypes.Structure):
+    """pas_scene_view (include/pas_b200.h)."""
+    _fields_ = [("camera", ctypes.c_double * 3), ("earth_center", ctypes.c_double * 3),
+                ("sun_direction", ctypes.c_double * 3), ("sun_size", ctypes.c_double * 2),
+                ("sphere_center", ctypes.c_double * 3), ("sphere_radius", ctypes.c_double),
+                ("model_from_clip", ctypes.c_double * 9), ("ground_albedo", ctypes.c_double * 3),
+                ("sphere_albedo", ctypes.c_double * 3), ("exposure", ctypes.c_double),
+                ("use_luminance", ctypes.c_int), ("width", ctypes.c_int), ("height", ctypes.c_int)]
+
+
 class _TextureInfo(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int) for n in
                 ("width", "height", "depth", "channels", "bytes_per_channel", "present")]
@@ -101,6 +111,18 @@ def load_library() -> ctypes.CDLL:
         lib.pas_model_attach_world.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
         lib.pas_world_is_cached.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int]
         lib.pas_release_cached_memory.restype = None
+        _FP = ctypes.POINTER(ctypes.c_float)
+        lib.pas_model_get_solar_radiance.argtypes = [ctypes.c_void_p, ctypes.c_int, _DP]
+        lib.pas_model_get_sky_radiance.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t,
+                                                   ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                                   ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+        lib.pas_model_get_sky_radiance_to_point.argtypes = lib.pas_model_get_sky_radiance.argtypes
+        lib.pas_model_get_sun_and_sky_irradiance.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t,
+                                                             ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                                             ctypes.c_void_p, ctypes.c_void_p]
+        lib.pas_model_render_scene.argtypes = [ctypes.c_void_p, ctypes.POINTER(_SceneView), ctypes.c_void_p,
+                                               ctypes.c_void_p]
+        lib.pas_model_last_render_ms.argtypes = [ctypes.c_void_p, _FP]
         _lib = lib
     return _lib
 
@@ -249,6 +271,75 @@ class Model:
         buf = ctypes.create_string_buffer(size.value)
         _check(self._lib.pas_model_shader_source(self._h, glsl_directory.encode(), buf, ctypes.byref(size)))
         return buf.value.decode()
+
+    # -- render-time API (atmosphere/reference/model.h:62-77; GLSL API of atmosphere/model.cc:221-281) --
+    @staticmethod
+    def _vec3(v, n=None) -> np.ndarray:
+        a = np.ascontiguousarray(np.asarray(v, dtype=np.float64))
+        if a.ndim == 1:
+            a = np.ascontiguousarray(np.broadcast_to(a, ((n or 1), 3)))
+        assert a.shape[-1] == 3
+        return a
+
+    def GetSolarRadiance(self, use_luminance: bool = False) -> np.ndarray:
+        out = (ctypes.c_double * 3)()
+        _check(self._lib.pas_model_get_solar_radiance(self._h, int(use_luminance), out))
+        return np.array(list(out))
+
+    def _sky(self, fn, camera, target, shadow_length, sun_direction, use_luminance):
+        cam = self._vec3(camera)
+        n = cam.shape[0]
+        tgt, sun = self._vec3(target, n), self._vec3(sun_direction, n)
+        sl = None
+        if shadow_length is not None:
+            sl = np.ascontiguousarray(np.broadcast_to(np.asarray(shadow_length, dtype=np.float64), (n,)))
+        rad, tr = np.empty((n, 3), np.float32), np.empty((n, 3), np.float32)
+        _check(fn(self._h, int(use_luminance), n, cam.ctypes.data, tgt.ctypes.data,
+                  sl.ctypes.data if sl is not None else None, sun.ctypes.data, rad.ctypes.data, tr.ctypes.data))
+        return rad, tr
+
+    def GetSkyRadiance(self, camera, view_ray, shadow_length, sun_direction, use_luminance: bool = False):
+        """Batched GetSkyRadiance (functions.glsl:1705-1769): arrays [n, 3]; returns (radiance,
+        transmittance), float32 [n, 3]."""
+        return self._sky(self._lib.pas_model_get_sky_radiance, camera, view_ray, shadow_length,
+                         sun_direction, use_luminance)
+
+    def GetSkyRadianceToPoint(self, camera, point, shadow_length, sun_direction, use_luminance: bool = False):
+        """Batched GetSkyRadianceToPoint (functions.glsl:1787-1863)."""
+        return self._sky(self._lib.pas_model_get_sky_radiance_to_point, camera, point, shadow_length,
+                         sun_direction, use_luminance)
+
+    def GetSunAndSkyIrradiance(self, point, normal, sun_direction, use_luminance: bool = False):
+        """Batched GetSunAndSkyIrradiance (functions.glsl:1878-1896): returns (sun, sky)."""
+        p = self._vec3(point)
+        n = p.shape[0]
+        nr, sun = self._vec3(normal, n), self._vec3(sun_direction, n)
+        e0, e1 = np.empty((n, 3), np.float32), np.empty((n, 3), np.float32)
+        _check(self._lib.pas_model_get_sun_and_sky_irradiance(self._h, int(use_luminance), n, p.ctypes.data,
+                                                             nr.ctypes.data, sun.ctypes.data, e0.ctypes.data,
+                                                             e1.ctypes.data))
+        return e0, e1
+
+    def render_scene(self, view, want_argb: bool = True):
+        """Renders the reference's test scene (reference/model_test.glsl) for a scene.SceneView.
+        Returns (rgb float32 [H, W, 3] before tone mapping, argb uint32 [H, W] or None)."""
+        v = _SceneView()
+        for name in ("camera", "earth_center", "sun_direction", "sun_size", "sphere_center",
+                     "model_from_clip", "ground_albedo", "sphere_albedo"):
+            vals = list(getattr(view, name))
+            getattr(v, name)[:] = vals
+        v.sphere_radius, v.exposure = view.sphere_radius, view.exposure
+        v.use_luminance, v.width, v.height = int(view.use_luminance), view.width, view.height
+        rgb = np.empty((view.height, view.width, 3), np.float32)
+        argb = np.empty((view.height, view.width), np.uint32) if want_argb else None
+        _check(self._lib.pas_model_render_scene(self._h, ctypes.byref(v), rgb.ctypes.data,
+                                                argb.ctypes.data if want_argb else None))
+        return rgb, argb
+
+    def last_render_ms(self) -> float:
+        ms = ctypes.c_float(0)
+        _check(self._lib.pas_model_last_render_ms(self._h, ctypes.byref(ms)))
+        return ms.value
 
     # -- tables ----------------------------------------------------------------------------------
     def texture_info(self, which: int) -> _TextureInfo:
