@@ -122,19 +122,213 @@ __device__ __forceinline__ void azimuth_sweep(Weights<ORDER2, NUM>& W, float x0,
   }
 }
 
+// ---- packed-fp32 formulation ---------------------------------------------------------------------
+// Same algorithm; the kernel above is bound by instruction issue (ncu: issue slots 79 % busy, FMA
+// pipe 65 %), so this one halves the number of FMA instructions with Blackwell's packed FFMA2
+// (fma.rn.f32x2, two independent fp32 FMAs per instruction, results identical to two FFMA):
+//  * sweep: the NUM - 1 ramps and the base term form NUM "entries", accumulated as NUM / 2 register
+//    pairs (entry NUM - 1 is the base: its "ramp" is the constant 1);
+//  * contraction: channels are processed in pairs; the tables are staged in shared memory with the
+//    two channels of a pair side by side, [l][pair][knot] float2, and the weights are broadcast to
+//    both halves;
+//  * the ground window is swept with 0, 2 or 4 ramps, whichever covers it (most directions that
+//    reach the ground see less than two irradiance texels).
+__device__ __forceinline__ float2 dup2(float v) { return make_float2(v, v); }
+template <bool ORDER2, int NUM, int NG>
+struct Weights2 {
+  // Entry i of a weight set pairs with element i of a staged row: i = 0 is the base (knot-0 value,
+  // "ramp" = 1), i >= 1 the ramp of knot difference i - 1. Entries 2h and 2h + 1 share a register pair.
+  // Order >= 3: set 0 pairs with the Rayleigh coefficient, set 1 with the Mie one.
+  // Order 2: sets 0..3 = (table R, coef R), (table R, coef M), (table M, coef R), (table M, coef M).
+  static constexpr int NW = ORDER2 ? 4 : 2;
+  float2 w[NW][NUM / 2];
+  float2 gb;                          // ORDER2: (sum pR, sum pM), base of the ground term
+  float2 g[2][NG > 0 ? NG / 2 : 1];   // ground ramps, coef R / coef M
+};
+
+template <bool ORDER2, int NUM, int NG>
+__device__ __forceinline__ void azimuth_sweep2(Weights2<ORDER2, NUM, NG>& W, float x0, float xc,
+                                               float xs, float n0, float nc_, float v0, float vc,
+                                               float vs, float gx0, float gxc, float gxs, float kR,
+                                               float kM, float kR1, float kM1, float g2p1, float m2g) {
+#pragma unroll
+  for (int m = 0; m < 16; ++m) {
+    const float c = kCosPhi[m], s = kSinPhi[m];
+    const float nu2 = fmaf(nc_, c, n0);
+    const float q = fmaf(nu2, nu2, 1.0f);
+    const float pR = kR * q;
+    const float rs = f_rsqrt(fmaf(m2g, nu2, g2p1));
+    const float pM = (kM * q) * (rs * rs) * rs;
+    const float2 pR2 = dup2(pR), pM2 = dup2(pM);
+    const float xb = fmaf(xc, c, x0);
+    const float xp = fmaf(xs, s, xb), xm = fmaf(-xs, s, xb);
+    if (!ORDER2) {
+#pragma unroll
+      for (int h = 0; h < NUM / 2; ++h) {
+        // entries 2h (ramp 2h - 1, or the base: counted once per cosine, doubled by the caller) and
+        // 2h + 1 (ramp 2h)
+        float2 cs;
+        cs.x = h == 0 ? 1.0f : f_sat(xp - (float)(2 * h - 1)) + f_sat(xm - (float)(2 * h - 1));
+        cs.y = f_sat(xp - (float)(2 * h)) + f_sat(xm - (float)(2 * h));
+        W.w[0][h] = __ffma2_rn(cs, pR2, W.w[0][h]);
+        W.w[1][h] = __ffma2_rn(cs, pM2, W.w[1][h]);
+      }
+    } else {
+      // order 2: incident radiance = R * P_R(nu1) + M * P_M(nu1) (functions.glsl:995-1003)
+      const float vb = fmaf(vc, c, v0);
+      const float nu1p = fmaf(vs, s, vb), nu1m = fmaf(-vs, s, vb);
+      const float q1p = fmaf(nu1p, nu1p, 1.0f), q1m = fmaf(nu1m, nu1m, 1.0f);
+      const float rp = f_rsqrt(fmaf(m2g, nu1p, g2p1)), rm = f_rsqrt(fmaf(m2g, nu1m, g2p1));
+      const float2 PRp2 = dup2(kR1 * q1p), PRm2 = dup2(kR1 * q1m);
+      const float2 PMp2 = dup2((kM1 * q1p) * (rp * rp) * rp), PMm2 = dup2((kM1 * q1m) * (rm * rm) * rm);
+#pragma unroll
+      for (int h = 0; h < NUM / 2; ++h) {
+        float2 cp, cm;
+        cp.x = h == 0 ? 1.0f : f_sat(xp - (float)(2 * h - 1));
+        cm.x = h == 0 ? 1.0f : f_sat(xm - (float)(2 * h - 1));
+        cp.y = f_sat(xp - (float)(2 * h));
+        cm.y = f_sat(xm - (float)(2 * h));
+        const float2 a = __ffma2_rn(cp, PRp2, __fmul2_rn(cm, PRm2));  // table R weight
+        const float2 b = __ffma2_rn(cp, PMp2, __fmul2_rn(cm, PMm2));  // table M weight
+        W.w[0][h] = __ffma2_rn(a, pR2, W.w[0][h]);
+        W.w[1][h] = __ffma2_rn(a, pM2, W.w[1][h]);
+        W.w[2][h] = __ffma2_rn(b, pR2, W.w[2][h]);
+        W.w[3][h] = __ffma2_rn(b, pM2, W.w[3][h]);
+      }
+      if (NG > 0) W.gb = __fadd2_rn(W.gb, make_float2(pR, pM));
+    }
+    if (NG > 0) {
+      const float gb = fmaf(gxc, c, gx0);
+      const float gp = fmaf(gxs, s, gb), gm = fmaf(-gxs, s, gb);
+#pragma unroll
+      for (int t = 0; t < NG; t += 2) {
+        float2 cs;
+        cs.x = f_sat(gp - (float)t) + f_sat(gm - (float)t);
+        cs.y = f_sat(gp - (float)(t + 1)) + f_sat(gm - (float)(t + 1));
+        W.g[0][t / 2] = __ffma2_rn(cs, pR2, W.g[0][t / 2]);
+        W.g[1][t / 2] = __ffma2_rn(cs, pM2, W.g[1][t / 2]);
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ float half_of(const float2& v, int i) { return i ? v.y : v.x; }
+
+// Contraction of 8 entries [CH0, CH0 + 8) of weight sets (2 TAB, 2 TAB + 1) with the staged rows of
+// table TAB, for every channel pair; the pass that holds entry 0 of table 0 also adds the ground term.
+template <int NP, bool ORDER2, int NUM, int NG, int TAB, int CH0>
+__device__ __forceinline__ void contract_pass(float2 (&acc)[NP], const Weights2<ORDER2, NUM, NG>& W,
+                                              const float2* __restrict__ row,
+                                              const float2* __restrict__ sG_l,
+                                              const float2* __restrict__ sCR,
+                                              const float2* __restrict__ sCM,
+                                              const float2* __restrict__ e0p,
+                                              const float2* __restrict__ dep, int e_pad) {
+  constexpr bool GROUND = NG > 0 && TAB == 0 && CH0 == 0;
+  float2 dR[8], dM[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int e = CH0 + i;
+    float r = half_of(W.w[2 * TAB][e / 2], e & 1), m = half_of(W.w[2 * TAB + 1][e / 2], e & 1);
+    // order >= 3: the base entry counted each cosine once; both signs of sin(phi) share it
+    if (!ORDER2 && e == 0) { r *= 2.0f; m *= 2.0f; }
+    dR[i] = dup2(r);
+    dM[i] = dup2(m);
+  }
+  float2 gbR2 = dR[0], gbM2 = dM[0];
+  float2 dgR[NG > 0 ? NG : 1], dgM[NG > 0 ? NG : 1];
+  if (GROUND) {
+    if (ORDER2) {
+      gbR2 = dup2(2.0f * W.gb.x);
+      gbM2 = dup2(2.0f * W.gb.y);
+    }
+#pragma unroll
+    for (int t = 0; t < NG; ++t) {
+      dgR[t] = dup2(half_of(W.g[0][t / 2], t & 1));
+      dgM[t] = dup2(half_of(W.g[1][t / 2], t & 1));
+    }
+  }
+#pragma unroll
+  for (int cp = 0; cp < NP; ++cp) {
+    float2 v[8];
+    const float4* r4 = reinterpret_cast<const float4*>(row + cp * NUM + CH0);
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+      const float4 t4 = r4[h];
+      v[2 * h] = make_float2(t4.x, t4.y);
+      v[2 * h + 1] = make_float2(t4.z, t4.w);
+    }
+    float2 tR = __fmul2_rn(v[0], dR[0]), tM = __fmul2_rn(v[0], dM[0]);
+#pragma unroll
+    for (int i = 1; i < 8; ++i) {
+      tR = __ffma2_rn(v[i], dR[i], tR);
+      tM = __ffma2_rn(v[i], dM[i], tM);
+    }
+    if (GROUND) {
+      const float2* e0 = e0p + cp * e_pad;
+      const float2* de = dep + cp * e_pad;
+      float2 eR = __fmul2_rn(e0[0], gbR2), eM = __fmul2_rn(e0[0], gbM2);
+#pragma unroll
+      for (int t = 0; t < NG; ++t) {
+        const float2 dv = de[t];
+        eR = __ffma2_rn(dv, dgR[t], eR);
+        eM = __ffma2_rn(dv, dgM[t], eM);
+      }
+      const float2 G2 = sG_l[cp];
+      tR = __ffma2_rn(G2, eR, tR);
+      tM = __ffma2_rn(G2, eM, tM);
+    }
+    acc[cp] = __ffma2_rn(sCR[cp], tR, __ffma2_rn(sCM[cp], tM, acc[cp]));
+  }
+}
+
+// One polar direction: sweep + contraction into acc[pair].
+template <int NP, bool ORDER2, int NUM, int NG>
+__device__ __forceinline__ void direction2(float2 (&acc)[NP], const float2* __restrict__ rowA,
+                                           const float2* __restrict__ rowB,
+                                           const float2* __restrict__ sG_l,
+                                           const float2* __restrict__ sCR,
+                                           const float2* __restrict__ sCM,
+                                           const float2* __restrict__ e0p,
+                                           const float2* __restrict__ dep, int e_pad, float x0,
+                                           float xc, float xs, float n0, float ncf, float v0, float vc,
+                                           float vs, float gx0, float gxc, float gxs, float kR,
+                                           float kM, float kR1, float kM1, float g2p1, float m2g) {
+  static_assert(NUM == 8 || NUM == 16, "entries are contracted in chunks of 8");
+  Weights2<ORDER2, NUM, NG> W;
+#pragma unroll
+  for (int a = 0; a < Weights2<ORDER2, NUM, NG>::NW; ++a) {
+#pragma unroll
+    for (int e = 0; e < NUM / 2; ++e) W.w[a][e] = make_float2(0.f, 0.f);
+  }
+  W.gb = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int t = 0; t < (NG > 0 ? NG / 2 : 1); ++t) W.g[0][t] = W.g[1][t] = make_float2(0.f, 0.f);
+  azimuth_sweep2<ORDER2, NUM, NG>(W, x0, xc, xs, n0, ncf, v0, vc, vs, gx0, gxc, gxs, kR, kM, kR1, kM1,
+                                  g2p1, m2g);
+  contract_pass<NP, ORDER2, NUM, NG, 0, 0>(acc, W, rowA, sG_l, sCR, sCM, e0p, dep, e_pad);
+  if (NUM == 16) contract_pass<NP, ORDER2, NUM, NG, 0, NUM - 8>(acc, W, rowA, sG_l, sCR, sCM, e0p, dep, e_pad);
+  if (ORDER2) {
+    contract_pass<NP, ORDER2, NUM, NG, ORDER2 ? 1 : 0, 0>(acc, W, rowB, sG_l, sCR, sCM, e0p, dep, e_pad);
+    if (NUM == 16) {
+      contract_pass<NP, ORDER2, NUM, NG, ORDER2 ? 1 : 0, NUM - 8>(acc, W, rowB, sG_l, sCR, sCM, e0p, dep, e_pad);
+    }
+  }
+}
+
 template <int NC, bool ORDER2, int NUM>
 __global__ void __launch_bounds__(256, 2)
-density_kernel(const __grid_constant__ PasGeometry g, const PasDensityDir* __restrict__ dirs,
-               const float* __restrict__ G, const float* __restrict__ cRk,
-               const float* __restrict__ cMk, const float* __restrict__ tabA,
-               const float* __restrict__ tabB, const float* __restrict__ dE,
-               float* __restrict__ dJ, int k_begin) {
-  constexpr int NT = ORDER2 ? 2 : 1;  // tables staged
-  constexpr int CP = PAS_CHANNEL_PITCH(NC);
+density_kernel_x2(const __grid_constant__ PasGeometry g, const PasDensityDir* __restrict__ dirs,
+                  const float* __restrict__ G, const float* __restrict__ cRk,
+                  const float* __restrict__ cMk, const float* __restrict__ tabA,
+                  const float* __restrict__ tabB, const float* __restrict__ dE,
+                  float* __restrict__ dJ, int k_begin) {
+  constexpr int NT = ORDER2 ? 2 : 1;
+  constexpr int CP = PAS_CHANNEL_PITCH(NC), NP = CP / 2;
   extern __shared__ __align__(16) float smem_dyn[];
-  __shared__ __align__(16) float sA[NT][PAS_DIR_THETA][NC][NUM];
-  __shared__ float sG[PAS_DIR_THETA][NC];
-  __shared__ float sCR[NC], sCM[NC];
+  __shared__ __align__(16) float2 sA[NT][PAS_DIR_THETA][NP][NUM];
+  __shared__ float2 sG[PAS_DIR_THETA][NP];
+  __shared__ float2 sCR[NP], sCM[NP];
   __shared__ DirConst sDir[PAS_DIR_THETA];
 
   const int tid = threadIdx.x;
@@ -143,10 +337,10 @@ density_kernel(const __grid_constant__ PasGeometry g, const PasDensityDir* __res
   const int mu_n = g.sz.mu_n, nu_n = g.sz.nu_n, mu_s_n = g.sz.mu_s_n, e_w = g.sz.e_w;
   const int width = nu_n * mu_s_n;
   const size_t layer = (size_t)k * mu_n * width;
-  // dynamic shared memory: irradiance row 0 and its forward differences, zero padded
+  // dynamic shared memory: irradiance row 0 and its forward differences, zero padded, channel pairs
   const int e_pad = e_w + kNG + 1;
-  float* sE0 = smem_dyn;              // [NC][e_pad]
-  float* sDE = smem_dyn + NC * e_pad; // [NC][e_pad]
+  float2* sE0 = reinterpret_cast<float2*>(smem_dyn);  // [NP][e_pad]
+  float2* sDE = sE0 + NP * e_pad;                     // [NP][e_pad]
 
   double r, rho;
   layer_radius(g, (k + 0.5) / g.sz.r_n, g.sz.r_n, &r, &rho);
@@ -159,15 +353,11 @@ density_kernel(const __grid_constant__ PasGeometry g, const PasDensityDir* __res
     dc.cos_t = d.cos_t;
     dc.sin_t = d.sin_t;
     dc.hit = d.hit;
-    // cosine at the ground point: (r mu_s + d_g nu1) / bottom  (|zenith r + omega_i d_g| = bottom,
-    // functions.glsl:1234-1238); irradiance texel x = (cos/2 + 1/2)(e_w - 1) (functions.glsl:1530-1531)
     const double half = 0.5 * (e_w - 1);
     const double ga = (r * mu_s_d / g.bottom) * half + half;
     const double gb = (double)d.dg_over_b * half;
     dc.g_a = (float)ga;
     dc.g_b = (float)gb;
-    // knots [i0, i1] cover every x the azimuth loop can produce (nu1 in [-1, 1]); x outside
-    // [0, e_w - 1] is clamped by the saturating ramps exactly like the fetch's index clamp
     int i0 = (int)floor(ga - gb - 1e-3);
     i0 = i0 < 0 ? 0 : (i0 > e_w - 2 ? e_w - 2 : i0);
     int i1 = (int)ceil(ga + gb + 1e-3);
@@ -177,41 +367,53 @@ density_kernel(const __grid_constant__ PasGeometry g, const PasDensityDir* __res
     dc.pad = 0;
     sDir[tid] = dc;
   }
-  if (tid < NC) {
-    sCR[tid] = cRk[k * PAS_MAX_CH + tid];
-    sCM[tid] = cMk[k * PAS_MAX_CH + tid];
-  }
-  for (int idx = tid; idx < PAS_DIR_THETA * NC; idx += blockDim.x) {
-    sG[idx / NC][idx % NC] = G[(size_t)(k * PAS_DIR_THETA + idx / NC) * PAS_MAX_CH + idx % NC];
-  }
-  for (int idx = tid; idx < NC * e_pad; idx += blockDim.x) {
-    const int c = idx / e_pad, i = idx % e_pad;
-    const float* row = dE + (size_t)c * e_w * g.sz.e_h;  // row 0: r = bottom
-    sE0[idx] = i < e_w ? row[i] : 0.f;
-    sDE[idx] = i < e_w - 1 ? row[i + 1] - row[i] : 0.f;
-  }
-  // mu-interpolated rows: value at slab s, then in place -> (V[0], D[0..NUM-2]). Consecutive
-  // threads read the consecutive channels of one interleaved texel (64 B at 15 channels).
-  for (int idx = tid; idx < NT * PAS_DIR_THETA * NUM * NC; idx += blockDim.x) {
-    const int c = idx % NC, s = (idx / NC) % NUM, l = (idx / (NC * NUM)) % PAS_DIR_THETA;
-    const int t = idx / (NC * NUM * PAS_DIR_THETA);
-    float v = 0.f;
-    if (s < nu_n) {
-      const PasDensityDir d = dirs[k * PAS_DIR_THETA + l];
-      const float* tab = (t == 0 ? tabA : tabB) + (layer + s * mu_s_n + i_mu_s) * CP + c;
-      const float a = tab[(size_t)d.j0 * width * CP], b = tab[(size_t)d.j1 * width * CP];
-      v = fmaf(d.w_row, b - a, a);
+  {
+    float* fCR = reinterpret_cast<float*>(sCR);
+    float* fCM = reinterpret_cast<float*>(sCM);
+    if (tid < CP) {
+      fCR[tid] = tid < NC ? cRk[k * PAS_MAX_CH + tid] : 0.f;
+      fCM[tid] = tid < NC ? cMk[k * PAS_MAX_CH + tid] : 0.f;
     }
-    sA[t][l][c][s] = v;
+    float* fG = reinterpret_cast<float*>(sG);
+    for (int idx = tid; idx < PAS_DIR_THETA * CP; idx += blockDim.x) {
+      const int l = idx / CP, c = idx % CP;
+      fG[idx] = c < NC ? G[(size_t)(k * PAS_DIR_THETA + l) * PAS_MAX_CH + c] : 0.f;
+    }
+    float* fE0 = reinterpret_cast<float*>(sE0);
+    float* fDE = reinterpret_cast<float*>(sDE);
+    for (int idx = tid; idx < CP * e_pad; idx += blockDim.x) {
+      const int c = idx / e_pad, i = idx % e_pad;
+      const float* row = dE + (size_t)c * e_w * g.sz.e_h;  // row 0: r = bottom
+      const int o = ((c >> 1) * e_pad + i) * 2 + (c & 1);
+      fE0[o] = (c < NC && i < e_w) ? row[i] : 0.f;
+      fDE[o] = (c < NC && i < e_w - 1) ? row[i + 1] - row[i] : 0.f;
+    }
+    // mu-interpolated rows: value at slab s, then in place -> (V[0], D[0..NUM-2]). Consecutive
+    // threads read the consecutive channels of one interleaved texel (64 B at 15 channels).
+    float* fA = reinterpret_cast<float*>(sA);
+    for (int idx = tid; idx < NT * PAS_DIR_THETA * NUM * CP; idx += blockDim.x) {
+      const int c = idx % CP, s = (idx / CP) % NUM, l = (idx / (CP * NUM)) % PAS_DIR_THETA;
+      const int t = idx / (CP * NUM * PAS_DIR_THETA);
+      float v = 0.f;
+      if (s < nu_n && c < NC) {
+        const PasDensityDir d = dirs[k * PAS_DIR_THETA + l];
+        const float* tab = (t == 0 ? tabA : tabB) + (layer + s * mu_s_n + i_mu_s) * CP + c;
+        const float a = tab[(size_t)d.j0 * width * CP], b = tab[(size_t)d.j1 * width * CP];
+        v = fmaf(d.w_row, b - a, a);
+      }
+      fA[((((t * PAS_DIR_THETA + l) * NP + (c >> 1)) * NUM) + s) * 2 + (c & 1)] = v;
+    }
   }
   __syncthreads();
-  for (int row = tid; row < NT * PAS_DIR_THETA * NC; row += blockDim.x) {
-    float* p = (&sA[0][0][0][0]) + row * NUM;
-    float v[NUM];
+  for (int row = tid; row < NT * PAS_DIR_THETA * NP; row += blockDim.x) {
+    float2* p = (&sA[0][0][0][0]) + row * NUM;
+    float2 v[NUM];
 #pragma unroll
     for (int s = 0; s < NUM; ++s) v[s] = p[s];
 #pragma unroll
-    for (int s = 0; s < NUM - 1; ++s) p[1 + s] = (s + 1 < nu_n) ? v[s + 1] - v[s] : 0.f;
+    for (int s = 0; s < NUM - 1; ++s) {
+      p[1 + s] = (s + 1 < nu_n) ? make_float2(v[s + 1].x - v[s].x, v[s + 1].y - v[s].y) : make_float2(0.f, 0.f);
+    }
   }
   __syncthreads();
 
@@ -223,7 +425,6 @@ density_kernel(const __grid_constant__ PasGeometry g, const PasDensityDir* __res
   bool hit_unused;
   scattering_row_mu(g, r, rho, j, &mu_d, &r_mu_d, &hit_unused);
   const double nu_d = scattering_slab_nu(g, i_nu, mu_d, mu_s_d);
-  // omega = (sqrt(1 - mu^2), 0, mu), omega_s = (sx, sy, mu_s) (functions.glsl:1181-1185)
   const double wx_d = sqrt(1.0 - mu_d * mu_d);
   const double sx_d = wx_d == 0.0 ? 0.0 : (nu_d - mu_d * mu_s_d) / wx_d;
   const double sy_d = sqrt(d_pos(1.0 - sx_d * sx_d - mu_s_d * mu_s_d));
@@ -237,117 +438,62 @@ density_kernel(const __grid_constant__ PasGeometry g, const PasDensityDir* __res
   const float kM1 = (float)mie_phase_k(g.mie_g);
   const float dtheta_dphi = (float)((kPi / PAS_DIR_THETA) * (kPi / PAS_DIR_THETA));
 
-  float acc[NC];
+  float2 acc[NP];
 #pragma unroll
-  for (int c = 0; c < NC; ++c) acc[c] = 0.f;
+  for (int c = 0; c < NP; ++c) acc[c] = make_float2(0.f, 0.f);
 
+#pragma unroll 1
   for (int l = 0; l < PAS_DIR_THETA; ++l) {
     const DirConst dc = sDir[l];
     const float ct = dc.cos_t, st = dc.sin_t;
     const float domega = dtheta_dphi * st;  // functions.glsl:1219
-    // nu1 = omega_s . omega_i = v0 + vc cos(phi) + vs sin(phi); x = (nu1 + 1) * scale
     const float v0 = mu_s * ct, vc = sx * st, vs = sy * st;
     const float x0 = fmaf(v0, scale, scale), xc = vc * scale, xs = vs * scale;
-    // nu2 = omega . omega_i = n0 + nc cos(phi)
     const float n0 = mu * ct, ncf = wx * st;
     const float kR = kR1 * domega, kM = kM1 * domega;
-
-    Weights<ORDER2, NUM> W;
-#pragma unroll
-    for (int a = 0; a < Weights<ORDER2, NUM>::NW; ++a) {
-      W.base[a] = 0.f;
-#pragma unroll
-      for (int s = 0; s < NUM - 1; ++s) W.ramp[a][s] = 0.f;
-    }
-    W.gbase[0] = W.gbase[1] = 0.f;
-#pragma unroll
-    for (int t = 0; t < kNG; ++t) W.gramp[0][t] = W.gramp[1][t] = 0.f;
-
-    // ground window in texel units relative to its first knot
     const float gx0 = fmaf(dc.g_b, v0, dc.g_a) - (float)dc.win_i0;
     const float gxc = dc.g_b * vc, gxs = dc.g_b * vs;
-    if (dc.win_n > 0) {
-      azimuth_sweep<ORDER2, NUM, true, true>(W, x0, xc, xs, n0, ncf, v0, vc, vs, gx0, gxc, gxs, kR,
-                                             kM, kR1, kM1, g2p1, m2g);
+    const float2* rowA = &sA[0][l][0][0];
+    const float2* rowB = &sA[NT - 1][l][0][0];
+    const float2* e0p = sE0 + dc.win_i0;
+    const float2* dep = sDE + dc.win_i0;
+    if (dc.win_n == 0) {
+      direction2<NP, ORDER2, NUM, 0>(acc, rowA, rowB, sG[l], sCR, sCM, e0p, dep, e_pad, x0, xc, xs, n0, ncf,
+                                     v0, vc, vs, gx0, gxc, gxs, kR, kM, kR1, kM1, g2p1, m2g);
+    } else if (dc.win_n <= 2) {
+      direction2<NP, ORDER2, NUM, 2>(acc, rowA, rowB, sG[l], sCR, sCM, e0p, dep, e_pad, x0, xc, xs, n0, ncf,
+                                     v0, vc, vs, gx0, gxc, gxs, kR, kM, kR1, kM1, g2p1, m2g);
     } else {
-      azimuth_sweep<ORDER2, NUM, false, true>(W, x0, xc, xs, n0, ncf, v0, vc, vs, gx0, gxc, gxs,
-                                              kR, kM, kR1, kM1, g2p1, m2g);
+      direction2<NP, ORDER2, NUM, 4>(acc, rowA, rowB, sG[l], sCR, sCM, e0p, dep, e_pad, x0, xc, xs, n0, ncf,
+                                     v0, vc, vs, gx0, gxc, gxs, kR, kM, kR1, kM1, g2p1, m2g);
     }
-    // gbase counted each cosine once; both signs of sin(phi) share it
-    const float gbR = 2.0f * W.gbase[0], gbM = 2.0f * W.gbase[1];
-
-    // ---- contraction with the spectral tables (broadcast shared-memory reads) ---------------
-#pragma unroll
-    for (int c = 0; c < NC; ++c) {
-      float tR, tM;
-      {
-        const float4* rowA = reinterpret_cast<const float4*>(&sA[0][l][c][0]);
-        float vA[NUM];
-#pragma unroll
-        for (int q4 = 0; q4 < NUM / 4; ++q4) {
-          const float4 t4 = rowA[q4];
-          vA[4 * q4] = t4.x; vA[4 * q4 + 1] = t4.y; vA[4 * q4 + 2] = t4.z; vA[4 * q4 + 3] = t4.w;
-        }
-        if (!ORDER2) {
-          tR = vA[0] * gbR;
-          tM = vA[0] * gbM;
-#pragma unroll
-          for (int s = 0; s < NUM - 1; ++s) {
-            tR = fmaf(vA[1 + s], W.ramp[0][s], tR);
-            tM = fmaf(vA[1 + s], W.ramp[1][s], tM);
-          }
-        } else {
-          const float4* rowB = reinterpret_cast<const float4*>(&sA[NT - 1][l][c][0]);
-          float vB[NUM];
-#pragma unroll
-          for (int q4 = 0; q4 < NUM / 4; ++q4) {
-            const float4 t4 = rowB[q4];
-            vB[4 * q4] = t4.x; vB[4 * q4 + 1] = t4.y; vB[4 * q4 + 2] = t4.z; vB[4 * q4 + 3] = t4.w;
-          }
-          tR = fmaf(vA[0], W.base[0], vB[0] * W.base[2]);
-          tM = fmaf(vA[0], W.base[1], vB[0] * W.base[3]);
-#pragma unroll
-          for (int s = 0; s < NUM - 1; ++s) {
-            tR = fmaf(vA[1 + s], W.ramp[0][s], tR);
-            tM = fmaf(vA[1 + s], W.ramp[1][s], tM);
-            tR = fmaf(vB[1 + s], W.ramp[2][s], tR);
-            tM = fmaf(vB[1 + s], W.ramp[3][s], tM);
-          }
-        }
-      }
-      if (dc.win_n > 0) {
-        const float* e0 = sE0 + c * e_pad + dc.win_i0;
-        const float* de = sDE + c * e_pad + dc.win_i0;
-        float eR = e0[0] * gbR, eM = e0[0] * gbM;
-#pragma unroll
-        for (int t = 0; t < kNG; ++t) {
-          eR = fmaf(de[t], W.gramp[0][t], eR);
-          eM = fmaf(de[t], W.gramp[1][t], eM);
-        }
-        tR = fmaf(sG[l][c], eR, tR);
-        tM = fmaf(sG[l][c], eM, tM);
-      }
-      acc[c] = fmaf(sCR[c], tR, fmaf(sCM[c], tM, acc[c]));
-    }
-
     // ---- wide ground windows (grazing rays, small planets): extra sweeps, kNG ramps each -----
     for (int w0 = kNG; w0 < dc.win_n; w0 += kNG) {
+      Weights<ORDER2, NUM> W;
       W.gbase[0] = W.gbase[1] = 0.f;
 #pragma unroll
       for (int t = 0; t < kNG; ++t) W.gramp[0][t] = W.gramp[1][t] = 0.f;
       azimuth_sweep<ORDER2, NUM, true, false>(W, x0, xc, xs, n0, ncf, v0, vc, vs, gx0 - (float)w0,
                                               gxc, gxs, kR, kM, kR1, kM1, g2p1, m2g);
+      float2 dgR[kNG], dgM[kNG];
 #pragma unroll
-      for (int c = 0; c < NC; ++c) {
-        const float* de = sDE + c * e_pad + dc.win_i0 + w0;
-        float eR = 0.f, eM = 0.f;
+      for (int t = 0; t < kNG; ++t) {
+        dgR[t] = dup2(W.gramp[0][t]);
+        dgM[t] = dup2(W.gramp[1][t]);
+      }
+#pragma unroll
+      for (int cp = 0; cp < NP; ++cp) {
+        const float2* de = dep + cp * e_pad + w0;
+        float2 eR = make_float2(0.f, 0.f), eM = make_float2(0.f, 0.f);
 #pragma unroll
         for (int t = 0; t < kNG; ++t) {
           // ramps past the last knot read the zero padding of sDE
-          eR = fmaf(de[t], W.gramp[0][t], eR);
-          eM = fmaf(de[t], W.gramp[1][t], eM);
+          const float2 dv = de[t];
+          eR = __ffma2_rn(dv, dgR[t], eR);
+          eM = __ffma2_rn(dv, dgM[t], eM);
         }
-        acc[c] = fmaf(sCR[c] * sG[l][c], eR, fmaf(sCM[c] * sG[l][c], eM, acc[c]));
+        const float2 G2 = sG[l][cp];
+        acc[cp] = __ffma2_rn(__fmul2_rn(sCR[cp], G2), eR, __ffma2_rn(__fmul2_rn(sCM[cp], G2), eM, acc[cp]));
       }
     }
   }
@@ -356,10 +502,7 @@ density_kernel(const __grid_constant__ PasGeometry g, const PasDensityDir* __res
   float4* out = reinterpret_cast<float4*>(dJ + (layer + (size_t)j * width + i_nu * mu_s_n + i_mu_s) * CP);
 #pragma unroll
   for (int q = 0; q < CP / 4; ++q) {
-    float v[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) v[e] = (4 * q + e < NC) ? acc[(4 * q + e < NC) ? 4 * q + e : 0] : 0.f;
-    out[q] = make_float4(v[0], v[1], v[2], v[3]);
+    out[q] = make_float4(acc[2 * q].x, acc[2 * q].y, acc[2 * q + 1].x, acc[2 * q + 1].y);
   }
 }
 
@@ -370,8 +513,9 @@ cudaError_t launch_one(const PasGeometry& g, const PasDensityDir* dirs, const fl
   const int threads = 256;
   const int texels = g.sz.mu_n * g.sz.nu_n;
   dim3 grid((texels + threads - 1) / threads, g.sz.mu_s_n, k_end - k_begin);
-  const size_t dyn = (size_t)2 * NC * (g.sz.e_w + kNG + 1) * sizeof(float);
-  auto kern = density_kernel<NC, ORDER2, NUM>;
+  constexpr int CP = PAS_CHANNEL_PITCH(NC);
+  const size_t dyn = (size_t)2 * CP * (g.sz.e_w + kNG + 1) * sizeof(float);
+  auto kern = density_kernel_x2<NC, ORDER2, NUM>;
   if (dyn > 16 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
     if (e != cudaSuccess) return e;

@@ -18,8 +18,6 @@
 //           sun-direction mu): 2-4 texel reads (128-bit, XOR-swizzled so that neighbouring
 //           texels fall in different banks) instead of 16 L2 gathers per channel.
 // The stage buffer is double buffered: one __syncthreads per sample.
-#include <cstdlib>
-
 #include "pas_kernels.h"
 #include "pas_physics.cuh"
 
@@ -339,9 +337,238 @@ multiple_scattering_kernel(const __grid_constant__ PasGeometry g,
              fin.half_precision, true);
 }
 
+// ---- multiple scattering, reference row width (256 texels = block size) -------------------------
+// Same mapping as above, with two changes that cut the L1 data-pipe wavefronts (the bound of this
+// kernel):
+//  * row slots: consecutive samples of a ray share on average 2.5 of their 4 (layer, mu) corner rows.
+//    Every thread keeps its 16-byte vectors of four rows in registers ("slots"); a per-block plan
+//    (built once, sequentially, by thread 0) says for every sample which row each slot must hold,
+//    with which weight, and which slots have to be (re)loaded. Rows that stay are not read again;
+//    the loads of sample i + 1 are issued right after the combine of sample i and land while the
+//    block gathers sample i.
+//  * texels whose nu lies exactly on a slab (about 70 %: every texel whose nu is not clamped,
+//    functions.glsl:923-925) need 2 instead of 4 texel reads per sample. The block's texels are
+//    permuted so that those come first and whole warps take the short path (bit-identical: the
+//    skipped terms are exact zeros).
+struct __align__(16) SlotSample {
+  int row[4];       // row offset (in texels) held by each slot during this sample
+  float w[4];       // weight of each slot
+  float d, inv_r;
+  int mask;         // slots to load before this sample's combine
+  int pad;
+};
+
+template <int NC>
+__global__ void __launch_bounds__(256, 2)
+multiple_scattering_rows_kernel(const __grid_constant__ PasGeometry g,
+                                const __grid_constant__ PasSpectrum sp, const float* __restrict__ T,
+                                const float* __restrict__ dJ, float* __restrict__ dS,
+                                FinalTables fin, int k_begin) {
+  constexpr int CP = PAS_CHANNEL_PITCH(NC), Q = CP / 4, WIDTH = 256;
+  static_assert(sizeof(SlotSample) == sizeof(ScatterSample), "plan is rewritten in place");
+  extern __shared__ __align__(16) float smem_dyn[];
+  __shared__ ScatterSample sSample[kSamples];
+  __shared__ __align__(16) float sTw[kSamples][CP];
+  __shared__ int sPerm[WIDTH];
+  __shared__ int sCount[WIDTH / 32];
+
+  const int tid = threadIdx.x;
+  const int j = blockIdx.x, k = k_begin + blockIdx.y;
+  const int mu_n = g.sz.mu_n, nu_n = g.sz.nu_n, mu_s_n = g.sz.mu_s_n;
+  constexpr int pitch = ((WIDTH + 7) & ~7) + 8 / Q;
+  float4* sRow = reinterpret_cast<float4*>(smem_dyn);  // [2][Q * pitch]
+  const float4* dJ4 = reinterpret_cast<const float4*>(dJ);
+
+  const BlockRay ray = block_ray(g, k, j);
+  if (tid < kSamples) {
+    ray_sample_setup<NC>(g, T, ray.r, ray.rho, ray.mu, ray.hit, ray.d_end, tid, &sSample[tid], sTw[tid]);
+  }
+
+  // ---- permutation: texels with nu on a slab first ---------------------------------------------
+  {
+    const int i_nu = tid / mu_s_n, i_mu_s = tid % mu_s_n;
+    const double nu_d = scattering_slab_nu(g, i_nu, ray.mu, scattering_col_mu_s(g, i_mu_s));
+    const Tap t = make_tap((nu_d + 1.0) * 0.5 * (nu_n - 1), nu_n);
+    const bool on_slab = t.w == 0.0f || t.w == 1.0f || t.i0 == t.i1;
+    const unsigned ballot = __ballot_sync(0xffffffffu, on_slab);
+    const int lane = tid & 31, warp = tid >> 5;
+    if (lane == 0) sCount[warp] = __popc(ballot);
+    __syncthreads();
+    int before = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < WIDTH / 32; ++w) {
+      const int c = sCount[w];
+      before += w < warp ? c : 0;
+      total += c;
+    }
+    const int rank_in_warp = __popc(ballot & ((1u << lane) - 1u));
+    // on-slab texels keep their relative order in [0, total); the others follow in [total, WIDTH)
+    const int pos = on_slab ? before + rank_in_warp : total + (warp * 32 - before) + (lane - rank_in_warp);
+    sPerm[pos] = tid;
+  }
+  // ---- slot plan ---------------------------------------------------------------------------------
+  // Row (layer k, mu row j) always lives in slot 2 (k & 1) + (j & 1): the four corner rows of a sample
+  // fall in four different slots, and a row shared with the previous sample is found where it was.
+  __syncthreads();
+  SlotSample mine;
+  if (tid < kSamples) {
+    const ScatterSample s = load_sample(&sSample[tid]);
+    const int rows[4] = {s.row00, s.row01, s.row10, s.row11};
+    const float ws[4] = {s.w00, s.w01, s.w10, s.w11};
+#pragma unroll
+    for (int t = 0; t < 4; ++t) { mine.row[t] = -1; mine.w[t] = 0.f; }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int rj = rows[c] / WIDTH;              // k * mu_n + j (mu_n is even)
+      const int slot = 2 * ((rj / mu_n) & 1) + (rj & 1);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        if (slot == t) { mine.row[t] = rows[c]; mine.w[t] += ws[c]; }  // clamped taps name a row twice
+      }
+    }
+    mine.d = s.d;
+    mine.inv_r = s.inv_r;
+    mine.pad = 0;
+  }
+  __syncthreads();  // every sample has been read in its first form
+  SlotSample* plan_w = reinterpret_cast<SlotSample*>(sSample);
+  if (tid < kSamples) {
+    mine.mask = 0;
+    plan_w[tid] = mine;
+  }
+  __syncthreads();
+  if (tid < kSamples) {
+    // a slot is (re)loaded when the previous sample left another row in it (or did not use it); a
+    // slot this sample does not use (row -1, weight 0) keeps its registers, whatever they hold
+    int mask = 0;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int prev = tid > 0 ? plan_w[tid - 1].row[t] : -1;
+      if (mine.row[t] >= 0 && mine.row[t] != prev) mask |= 1 << t;
+    }
+    plan_w[tid].mask = mask;
+  }
+  __syncthreads();
+  const SlotSample* plan = reinterpret_cast<const SlotSample*>(sSample);
+
+  // per-thread axes: mu_s (column) and nu (slab) of the texel this thread owns
+  const int x = sPerm[tid];
+  const int i_nu = x / mu_s_n, i_mu_s = x % mu_s_n;
+  const double mu_s_d = scattering_col_mu_s(g, i_mu_s);
+  const double nu_d = scattering_slab_nu(g, i_nu, ray.mu, mu_s_d);
+  const float nu = (float)nu_d;
+  const float r_mu_s = (float)(ray.r * mu_s_d);
+  const float bottom = (float)g.bottom;
+  const Tap tnu = make_tap((nu_d + 1.0) * 0.5 * (nu_n - 1), nu_n);
+  const int slab0 = tnu.i0 * mu_s_n, slab1 = tnu.i1 * mu_s_n;
+  const float wnu = tnu.w;
+  const bool on_slab = wnu == 0.0f || wnu == 1.0f || tnu.i0 == tnu.i1;
+  const bool warp_on_slab = __all_sync(0xffffffffu, on_slab);
+  const int slab_s = wnu == 1.0f ? slab1 : slab0;
+  MuSMap map;
+  map.H2 = (float)(g.H * g.H);
+  map.d_min = (float)(g.top - g.bottom);
+  map.inv_range = (float)(1.0 / (g.H - (g.top - g.bottom)));
+  map.inv_A = (float)(1.0 / g.mus_A);
+  map.scale = (float)(mu_s_n - 1);
+
+  float4 acc[Q];
+#pragma unroll
+  for (int q = 0; q < Q; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+  if (ray.d_end > 0.0) {
+    float4 R0[Q], R1[Q], R2[Q], R3[Q];
+#pragma unroll
+    for (int it = 0; it < Q; ++it) R0[it] = R1[it] = R2[it] = R3[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+    // flat vector f = tid + it * WIDTH of a row: plane f % Q = tid % Q, texel f / Q = tid / Q + it * (WIDTH / Q)
+    float4* const dst0 = sRow + (tid % Q) * pitch + tid / Q;
+#define PAS_LOAD_SLOTS(S)                                                                \
+    {                                                                                    \
+      if ((S).mask & 1) { const float4* p = dJ4 + (size_t)(S).row[0] * Q + tid;          \
+        _Pragma("unroll") for (int it = 0; it < Q; ++it) R0[it] = __ldg(p + it * WIDTH); } \
+      if ((S).mask & 2) { const float4* p = dJ4 + (size_t)(S).row[1] * Q + tid;          \
+        _Pragma("unroll") for (int it = 0; it < Q; ++it) R1[it] = __ldg(p + it * WIDTH); } \
+      if ((S).mask & 4) { const float4* p = dJ4 + (size_t)(S).row[2] * Q + tid;          \
+        _Pragma("unroll") for (int it = 0; it < Q; ++it) R2[it] = __ldg(p + it * WIDTH); } \
+      if ((S).mask & 8) { const float4* p = dJ4 + (size_t)(S).row[3] * Q + tid;          \
+        _Pragma("unroll") for (int it = 0; it < Q; ++it) R3[it] = __ldg(p + it * WIDTH); } \
+    }
+    SlotSample s = load_sample(&plan[0]);
+    PAS_LOAD_SLOTS(s)
+    for (int i = 0; i < kSamples; ++i) {
+      float4* buf = sRow + (i & 1) * Q * pitch;
+      float4* dst = dst0 + (i & 1) * Q * pitch;
+#pragma unroll
+      for (int it = 0; it < Q; ++it) {
+        dst[it * (WIDTH / Q)] = combine4(s.w[0], R0[it], s.w[1], R1[it], s.w[2], R2[it], s.w[3], R3[it]);
+      }
+      const float s_d = s.d, s_inv_r = s.inv_r;
+      if (i + 1 < kSamples) {
+        s = load_sample(&plan[i + 1]);
+        PAS_LOAD_SLOTS(s)
+      }
+      __syncthreads();
+      // mu_s at the sample: (r mu_s + d nu) / r_i (functions.glsl:1314)
+      const float mu_s_i = f_clamp(fmaf(s_d, nu, r_mu_s) * s_inv_r, -1.0f, 1.0f);
+      const float xs = f_clamp(f_mu_s_texel_x(map, bottom * mu_s_i), 0.0f, map.scale);
+      const Tap tm = make_tap_f(xs, mu_s_n);
+      const float wm = tm.w;
+      const float4* tw4 = reinterpret_cast<const float4*>(sTw[i]);
+      if (warp_on_slab) {
+        const float4* a0 = buf + slab_s + tm.i0;
+        const float4* a1 = buf + slab_s + tm.i1;
+        const float w0 = 1.0f - wm;
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+          const float4 u = a0[q * pitch], v = a1[q * pitch];
+          fma4(acc[q], make_float4(fmaf(w0, u.x, wm * v.x), fmaf(w0, u.y, wm * v.y),
+                                   fmaf(w0, u.z, wm * v.z), fmaf(w0, u.w, wm * v.w)), tw4[q]);
+        }
+      } else {
+        // the four corner weights of the (mu_s, nu) bilinear fetch
+        const float w11 = wnu * wm, w10 = wnu - w11, w01 = wm - w11, w00 = 1.0f - wnu - wm + w11;
+        const float4* a0 = buf + slab0 + tm.i0;
+        const float4* a1 = buf + slab0 + tm.i1;
+        const float4* b0 = buf + slab1 + tm.i0;
+        const float4* b1 = buf + slab1 + tm.i1;
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+          fma4(acc[q], combine4(w00, a0[q * pitch], w01, a1[q * pitch], w10, b0[q * pitch], w11, b1[q * pitch]),
+               tw4[q]);
+        }
+      }
+    }
+#undef PAS_LOAD_SLOTS
+  }
+  const size_t texel = ((size_t)k * mu_n + j) * WIDTH + x;
+  float4* out = reinterpret_cast<float4*>(dS) + texel * Q;
+  float rgb[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+  for (int q = 0; q < Q; ++q) {
+    out[q] = acc[q];
+    const float v[4] = {acc[q].x, acc[q].y, acc[q].z, acc[q].w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int c = 4 * q + e;
+      if (c < NC) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) rgb[a] = fmaf(sp.lum[a][c], v[e], rgb[a]);
+      }
+    }
+  }
+  // scattering += L . dS / RayleighPhaseFunction(nu) (model.cc:204-207), alpha += 0
+  const float inv_pr = (float)(1.0 / rayleigh_phase(nu_d));
+  final_rgba(fin.scattering, texel, make_float4(rgb[0] * inv_pr, rgb[1] * inv_pr, rgb[2] * inv_pr, 0.f),
+             fin.half_precision, true);
+}
+
 // ---- single scattering ------------------------------------------------------------------------
 // WIDTH > 0: nu_n * mu_s_n == t_w == WIDTH == block size.
-template <int NC, int MAXT, int MINB, int WIDTH>
+// NU_LANES (WIDTH > 0 only): consecutive threads own the nu slabs of one mu_s column instead of the
+// mu_s columns of one slab. The sun lookups of neighbouring lanes then fall on the same or on
+// neighbouring transmittance texels (they differ by d nu / r_i only), which the 128-bit shared loads
+// serve without bank conflicts; the staged row is stored unrotated.
+template <int NC, int MAXT, int MINB, int WIDTH, bool NU_LANES>
 __global__ void __launch_bounds__(MAXT, MINB)
 single_scattering_kernel(const __grid_constant__ PasGeometry g,
                          const __grid_constant__ PasSpectrum sp, const float* __restrict__ T,
@@ -366,7 +593,7 @@ single_scattering_kernel(const __grid_constant__ PasGeometry g,
   if (tid < kSamples) {
     ray_sample_setup<NC>(g, T, ray.r, ray.rho, ray.mu, ray.hit, ray.d_end, tid, &sSample[tid], sTw[tid]);
   }
-  const int x = tid;
+  const int x = NU_LANES ? (tid % nu_n) * mu_s_n + tid / nu_n : tid;
   const bool active = x < width;
   const int i_nu = active ? x / mu_s_n : 0, i_mu_s = active ? x % mu_s_n : 0;
   const double mu_s_d = scattering_col_mu_s(g, i_mu_s);
@@ -374,6 +601,7 @@ single_scattering_kernel(const __grid_constant__ PasGeometry g,
   const float nu = (float)nu_d;
   const float r_mu_s = (float)(ray.r * mu_s_d);
   const float x_max = (float)(t_w - 1);
+  auto rot = [](int v) { return NU_LANES ? v : rot8(v); };
 
   float4 accR[Q], accM[Q];
 #pragma unroll
@@ -397,11 +625,11 @@ single_scattering_kernel(const __grid_constant__ PasGeometry g,
           }
 #pragma unroll
           for (int it = 0; it < Q; ++it) {
-            buf[(tid % Q) * pitch + rot8(tid / Q + it * (WIDTH / Q))] = lerp4(s.wy, a[it], b[it]);
+            buf[(tid % Q) * pitch + rot(tid / Q + it * (WIDTH / Q))] = lerp4(s.wy, a[it], b[it]);
           }
         } else {
           for (int f = tid; f < t_w * Q; f += nthreads) {
-            buf[(f % Q) * pitch + rot8(f / Q)] = lerp4(s.wy, __ldg(pa + f), __ldg(pb + f));
+            buf[(f % Q) * pitch + rot(f / Q)] = lerp4(s.wy, __ldg(pa + f), __ldg(pb + f));
           }
         }
       }
@@ -417,8 +645,8 @@ single_scattering_kernel(const __grid_constant__ PasGeometry g,
         const float sm = f_sat(fmaf(mu_s_i - s.cos_h, s.inv_sun_w, 0.5f));
         const float vis = sm * sm * fmaf(-2.0f, sm, 3.0f);
         const float wr = vis * s.dens_r, wm = vis * s.dens_m;
-        const float4* t0 = buf + rot8(tu.i0);
-        const float4* t1 = buf + rot8(tu.i1);
+        const float4* t0 = buf + rot(tu.i0);
+        const float4* t1 = buf + rot(tu.i1);
         const float4* tw4 = reinterpret_cast<const float4*>(sTw[i]);
 #pragma unroll
         for (int q = 0; q < Q; ++q) {
@@ -492,8 +720,12 @@ cudaError_t launch_multiple_nc(const PasGeometry& g, const PasSpectrum& s, const
   const size_t dyn = (size_t)2 * Q * (((width + 7) & ~7) + 8 / Q) * sizeof(float4);
   const dim3 grid(g.sz.mu_n, k_end - k_begin);
   cudaError_t e;
-  if (width == 256) {
-    auto kern = multiple_scattering_kernel<NC, 256, 3, 256>;  // the reference's 8 x 32 row
+  if (width == 256 && Q > 1) {
+    auto kern = multiple_scattering_rows_kernel<NC>;  // the reference's 8 x 32 row
+    if ((e = prepare(kern, dyn)) != cudaSuccess) return e;
+    kern<<<grid, 256, dyn, stream>>>(g, s, T, dJ, dS, fin, k_begin);
+  } else if (width == 256) {
+    auto kern = multiple_scattering_kernel<NC, 256, 3, 256>;
     if ((e = prepare(kern, dyn)) != cudaSuccess) return e;
     kern<<<grid, 256, dyn, stream>>>(g, s, T, dJ, dS, fin, k_begin);
   } else if (threads <= 256) {
@@ -520,15 +752,15 @@ cudaError_t launch_single_nc(const PasGeometry& g, const PasSpectrum& s, const f
   const dim3 grid(g.sz.mu_n, k_end - k_begin);
   cudaError_t e;
   if (width == 256 && g.sz.t_w == 256) {
-    auto kern = single_scattering_kernel<NC, 256, 3, 256>;
+    auto kern = single_scattering_kernel<NC, 256, 3, 256, true>;
     if ((e = prepare(kern, dyn)) != cudaSuccess) return e;
     kern<<<grid, 256, dyn, stream>>>(g, s, T, dR, dM, fin, k_begin);
   } else if (threads <= 256) {
-    auto kern = single_scattering_kernel<NC, 256, 3, 0>;
+    auto kern = single_scattering_kernel<NC, 256, 3, 0, false>;
     if ((e = prepare(kern, dyn)) != cudaSuccess) return e;
     kern<<<grid, threads, dyn, stream>>>(g, s, T, dR, dM, fin, k_begin);
   } else {
-    auto kern = single_scattering_kernel<NC, 1024, 1, 0>;
+    auto kern = single_scattering_kernel<NC, 1024, 1, 0, false>;
     if ((e = prepare(kern, dyn)) != cudaSuccess) return e;
     kern<<<grid, threads, dyn, stream>>>(g, s, T, dR, dM, fin, k_begin);
   }

@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <map>
@@ -251,6 +252,8 @@ struct pas_model {
   // ---- device state ----
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t aux = nullptr;       // side stream of Init: irradiance passes, final RGB transmittance
+  cudaEvent_t ev_main = nullptr, ev_aux = nullptr;
   DeviceBuffer T, dE, dR, dM, dJ, dS, dirs, G, cR, cM, T_rgb, scratch;
   DeviceBuffer S, M, E, T_rgba;
   DeviceBuffer render_in[4], render_out[2];  // staging of host-pointer render queries
@@ -491,7 +494,12 @@ pas_status allocate(pas_model* m) {
 }
 
 // One phase of Precompute (model.cc:1048-1215) for channel group `gi`.
-pas_status run_phase(pas_model* m, int gi, int phase, int order, bool accumulate) {
+// `stream`: where the phase is enqueued. `ds_in`: the table holding the previous order's multiple
+// scattering (read by the density and irradiance passes); `ds_out`: where the multiple-scattering
+// pass writes. The reference aliases both to one texture (model.cc:897); Init alternates two buffers
+// so that the irradiance pass of order n can overlap the multiple-scattering pass of order n.
+pas_status run_phase(pas_model* m, int gi, int phase, int order, bool accumulate, cudaStream_t stream,
+                     float* ds_in, float* ds_out) {
   const PasSpectrum& sp = m->groups[gi];
   const PasGeometry& g = m->geom;
   int k0, k1;
@@ -499,24 +507,24 @@ pas_status run_phase(pas_model* m, int gi, int phase, int order, bool accumulate
   pas::FinalTables fin = final_tables(m, accumulate);
   switch (phase) {
     case 0:
-      PAS_CUDA(pas::launch_transmittance(g, sp, m->T.f(), m->stream));
+      PAS_CUDA(pas::launch_transmittance(g, sp, m->T.f(), stream));
       PAS_CUDA(pas::launch_density_setup(g, sp, m->T.f(), static_cast<PasDensityDir*>(m->dirs.p),
-                                         m->G.f(), m->cR.f(), m->cM.f(), m->stream));
+                                         m->G.f(), m->cR.f(), m->cM.f(), stream));
       m->launches += 2;
       break;
     case 1:
-      PAS_CUDA(pas::launch_direct_irradiance(g, sp, m->T.f(), m->dE.f(), fin, m->stream));
+      PAS_CUDA(pas::launch_direct_irradiance(g, sp, m->T.f(), m->dE.f(), fin, stream));
       m->launches += 1;
       break;
     case 2:
       PAS_CUDA(pas::launch_single_scattering(g, sp, m->T.f(), m->dR.f(), m->dM.f(), fin, k0, k1,
-                                             m->stream));
+                                             stream));
       m->launches += 1;
       break;
     case 3:
       PAS_CUDA(pas::launch_scattering_density(
           g, sp, static_cast<const PasDensityDir*>(m->dirs.p), m->G.f(), m->cR.f(), m->cM.f(),
-          m->dR.f(), m->dM.f(), m->dS.f(), m->dE.f(), order, m->dJ.f(), k0, k1, m->stream));
+          m->dR.f(), m->dM.f(), ds_in, m->dE.f(), order, m->dJ.f(), k0, k1, stream));
       m->launches += 1;
       if (m->world > 1) {
         // all-gather of the density r-slabs over NVLink: every rank needs every layer its rays
@@ -529,19 +537,19 @@ pas_status run_phase(pas_model* m, int gi, int phase, int order, bool accumulate
           return fail(PAS_ERR_UNSUPPORTED, "scattering_r must be divisible by the world size");
         }
         PAS_NCCL(nccl().AllGather(m->dJ.f() + (size_t)k0 * lt, m->dJ.f(), (size_t)base * lt, ncclFloat,
-                                  m->comm, m->stream));
+                                  m->comm, stream));
       }
       break;
     case 4: {
       if (m->world > 1) fin.irradiance = nullptr;  // partial sums: accumulate after the all-reduce
-      PAS_CUDA(pas::launch_indirect_irradiance(g, sp, m->dR.f(), m->dM.f(), m->dS.f(), order,
-                                               m->dE.f(), fin, 0, g.sz.e_h, k0, k1, m->stream));
+      PAS_CUDA(pas::launch_indirect_irradiance(g, sp, m->dR.f(), m->dM.f(), ds_in, order,
+                                               m->dE.f(), fin, 0, g.sz.e_h, k0, k1, stream));
       m->launches += 1;
       if (m->world > 1) {
         PAS_NCCL(nccl().AllReduce(m->dE.f(), m->dE.f(), m->n_e() * sp.nc, ncclFloat, ncclSum,
-                                  m->comm, m->stream));
+                                  m->comm, stream));
         const int n = (int)m->n_e();
-        accumulate_irradiance_kernel<<<(n + 127) / 128, 128, 0, m->stream>>>(m->dE.f(), n, sp.nc, sp,
+        accumulate_irradiance_kernel<<<(n + 127) / 128, 128, 0, stream>>>(m->dE.f(), n, sp.nc, sp,
                                                                               m->E.f());
         PAS_CUDA(cudaGetLastError());
         m->launches += 1;
@@ -549,8 +557,8 @@ pas_status run_phase(pas_model* m, int gi, int phase, int order, bool accumulate
       break;
     }
     case 5:
-      PAS_CUDA(pas::launch_multiple_scattering(g, sp, m->T.f(), m->dJ.f(), m->dS.f(), fin, k0, k1,
-                                               m->stream));
+      PAS_CUDA(pas::launch_multiple_scattering(g, sp, m->T.f(), m->dJ.f(), ds_out, fin, k0, k1,
+                                               stream));
       m->launches += 1;
       break;
     default:
@@ -674,6 +682,15 @@ pas_status pas_model_create(const pas_model_params* p, pas_model** out) {
     PAS_CUDA(cudaGetDevice(&m->device));
   }
   PAS_CUDA(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+  {
+    // the side stream gets the higher priority: its small kernels (1024 blocks) are scheduled as
+    // soon as the big pass running beside them frees a slot
+    int lo = 0, hi = 0;
+    PAS_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    PAS_CUDA(cudaStreamCreateWithPriority(&m->aux, cudaStreamNonBlocking, hi));
+    PAS_CUDA(cudaEventCreateWithFlags(&m->ev_main, cudaEventDisableTiming));
+    PAS_CUDA(cudaEventCreateWithFlags(&m->ev_aux, cudaEventDisableTiming));
+  }
   st = allocate(m.get());
   if (st != PAS_OK) return st;
   *out = m.release();
@@ -686,6 +703,12 @@ void pas_model_destroy(pas_model* m) {
   if (m->stream) {
     cudaStreamSynchronize(m->stream);
   }
+  if (m->aux) {
+    cudaStreamSynchronize(m->aux);
+    cudaStreamDestroy(m->aux);
+  }
+  if (m->ev_main) cudaEventDestroy(m->ev_main);
+  if (m->ev_aux) cudaEventDestroy(m->ev_aux);
   if (m->stream) cudaStreamDestroy(m->stream);
   delete m;
 }
@@ -695,45 +718,77 @@ pas_status pas_model_init(pas_model* m, unsigned int num_scattering_orders) {
   if (num_scattering_orders < 1) return fail(PAS_ERR_INVALID_ARGUMENT, "need >= 1 scattering order");
   PAS_CUDA(cudaSetDevice(m->device));
   m->launches = 0;
+  // Overlapped schedule (single GPU, no captures): the irradiance pass of order n depends on the
+  // radiance of order n - 1 only, so it runs on the side stream beside the multiple-scattering pass
+  // of order n; so does the final RGB transmittance, beside everything. With captures (tests) or in
+  // a multi-GPU world every pass is enqueued on the one stream, in the reference's order.
+  static const bool no_overlap = getenv("PAS_NO_OVERLAP") != nullptr;
+  const bool overlap = !m->capture && m->world == 1 && !no_overlap;
+  cudaStream_t main = m->stream, side = overlap ? m->aux : m->stream;
+  auto side_after_main = [&]() -> cudaError_t {
+    if (!overlap) return cudaSuccess;
+    cudaError_t e = cudaEventRecord(m->ev_main, main);
+    return e != cudaSuccess ? e : cudaStreamWaitEvent(side, m->ev_main, 0);
+  };
+  auto main_after_side = [&]() -> cudaError_t {
+    if (!overlap) return cudaSuccess;
+    cudaError_t e = cudaEventRecord(m->ev_aux, side);
+    return e != cudaSuccess ? e : cudaStreamWaitEvent(main, m->ev_aux, 0);
+  };
   PhaseTimer timer(m);
   timer.mark("start");
+  if (m->num_precomputed_wavelengths > 3) {
+    // final transmittance at 680/550/440 nm (model.cc:951-963): independent of everything else
+    PAS_CUDA(side_after_main());
+    PAS_CUDA(pas::launch_transmittance(m->geom, m->rgb_spectrum, m->T_rgb.f(), side));
+    PAS_CUDA(pas::launch_pack_rgba(m->T_rgb.f(), (int)m->n_t(), 3, m->T_rgba.f(), side));
+    m->launches += 2;
+    if (!overlap) timer.mark("final_transmittance");
+  }
   for (size_t gi = 0; gi < m->groups.size(); ++gi) {
     const bool blend = gi > 0;  // additive blending for batches after the first (model.cc:946-948)
     const int nc = m->groups[gi].nc, off = m->group_offset[gi];
     pas_status st;
-    if ((st = run_phase(m, (int)gi, 0, 0, blend)) != PAS_OK) return st;
+    float* const dS = m->dS.f();
+    if ((st = run_phase(m, (int)gi, 0, 0, blend, main, dS, dS)) != PAS_OK) return st;
     timer.mark("transmittance");
     if ((st = capture_copy(m, "transmittance", m->T.f(), m->n_t(), nc, off, true)) != PAS_OK) return st;
-    if ((st = run_phase(m, (int)gi, 1, 0, blend)) != PAS_OK) return st;
+    if ((st = run_phase(m, (int)gi, 1, 0, blend, main, dS, dS)) != PAS_OK) return st;
     timer.mark("direct_irradiance");
     if ((st = capture_copy(m, "delta_irradiance_1", m->dE.f(), m->n_e(), nc, off, false)) != PAS_OK) return st;
-    if ((st = run_phase(m, (int)gi, 2, 0, blend)) != PAS_OK) return st;
+    if ((st = run_phase(m, (int)gi, 2, 0, blend, main, dS, dS)) != PAS_OK) return st;
     timer.mark("single_scattering");
     if ((st = capture_copy(m, "delta_rayleigh", m->dR.f(), m->n_s(), nc, off, true)) != PAS_OK) return st;
     if ((st = capture_copy(m, "delta_mie", m->dM.f(), m->n_s(), nc, off, true)) != PAS_OK) return st;
+    // multiple scattering of order n is written to dS (n even) or, overlapped, to the then unused dR
+    // (n odd): the irradiance pass running beside it still reads the previous order
+    float* ds_in = dS;
     for (unsigned order = 2; order <= num_scattering_orders; ++order) {
       const std::string tag = std::to_string(order);
-      if ((st = run_phase(m, (int)gi, 3, (int)order, blend)) != PAS_OK) return st;
+      float* ds_out = (overlap && (order & 1)) ? m->dR.f() : dS;
+      // the density pass reads the irradiance of the previous order: join the side stream
+      PAS_CUDA(main_after_side());
+      if ((st = run_phase(m, (int)gi, 3, (int)order, blend, main, ds_in, ds_out)) != PAS_OK) return st;
       timer.mark("scattering_density_" + tag);
       if ((st = capture_copy(m, "delta_density_" + tag, m->dJ.f(), m->n_s(), nc, off, true)) != PAS_OK) return st;
-      // irradiance from the radiance of the previous order (model.cc:1187-1188)
-      if ((st = run_phase(m, (int)gi, 4, (int)order - 1, blend)) != PAS_OK) return st;
-      timer.mark("indirect_irradiance_" + tag);
+      // irradiance from the radiance of the previous order (model.cc:1187-1188); it overwrites the
+      // irradiance table the density pass has just read
+      PAS_CUDA(side_after_main());
+      if ((st = run_phase(m, (int)gi, 4, (int)order - 1, blend, side, ds_in, ds_out)) != PAS_OK) return st;
+      if (!overlap) timer.mark("indirect_irradiance_" + tag);
       if ((st = capture_copy(m, "delta_irradiance_" + tag, m->dE.f(), m->n_e(), nc, off, false)) != PAS_OK) return st;
-      if ((st = run_phase(m, (int)gi, 5, (int)order, blend)) != PAS_OK) return st;
+      if ((st = run_phase(m, (int)gi, 5, (int)order, blend, main, ds_in, ds_out)) != PAS_OK) return st;
       timer.mark("multiple_scattering_" + tag);
-      if ((st = capture_copy(m, "delta_multiple_" + tag, m->dS.f(), m->n_s(), nc, off, true)) != PAS_OK) return st;
+      if ((st = capture_copy(m, "delta_multiple_" + tag, ds_out, m->n_s(), nc, off, true)) != PAS_OK) return st;
+      ds_in = ds_out;
     }
+    // the next group restarts with the transmittance pass, which the side stream may still read
+    PAS_CUDA(main_after_side());
   }
-  // final transmittance at 680/550/440 nm (model.cc:951-963)
-  if (m->num_precomputed_wavelengths > 3) {
-    PAS_CUDA(pas::launch_transmittance(m->geom, m->rgb_spectrum, m->T_rgb.f(), m->stream));
-    PAS_CUDA(pas::launch_pack_rgba(m->T_rgb.f(), (int)m->n_t(), 3, m->T_rgba.f(), m->stream));
-  } else {
-    PAS_CUDA(pas::launch_pack_rgba(m->T.f(), (int)m->n_t(), 3, m->T_rgba.f(), m->stream));
-    m->launches -= 1;
+  if (m->num_precomputed_wavelengths <= 3) {
+    PAS_CUDA(pas::launch_pack_rgba(m->T.f(), (int)m->n_t(), 3, m->T_rgba.f(), main));
+    m->launches += 1;
   }
-  m->launches += 2;
   if (m->world > 1) {
     // every rank ends with the complete scattering table(s)
     int k0, k1;
@@ -955,7 +1010,7 @@ pas_status pas_model_run_phase(pas_model* m, int phase, int order) {
   if (m == nullptr) return fail(PAS_ERR_INVALID_ARGUMENT, "model is NULL");
   if (m->groups.size() != 1) return fail(PAS_ERR_UNSUPPORTED, "single passes need <= 16 channels");
   PAS_CUDA(cudaSetDevice(m->device));
-  pas_status st = run_phase(m, 0, phase, order, false);
+  pas_status st = run_phase(m, 0, phase, order, false, m->stream, m->dS.f(), m->dS.f());
   if (st != PAS_OK) return st;
   PAS_CUDA(cudaStreamSynchronize(m->stream));
   return PAS_OK;
