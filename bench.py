@@ -234,6 +234,7 @@ def run_b200(args, rank, world_size, local_rank):
     distributed = world_size > 1
     if distributed:
         import torch.distributed as dist
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     def barrier():
@@ -340,7 +341,10 @@ def run_b200(args, rank, world_size, local_rank):
         "wall_ms_per_step": round(wall_ms, 4), "higher_is_better": False, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "orders": ORDERS, "wavelengths": WAVELENGTHS,
-                   "parallelism": "1 GPU" if world_size == 1 else f"r-slabs over {world_size} GPUs, NCCL all-gather per order",
+                   "parallelism": "1 GPU" if world_size == 1 else (
+                       f"r-slabs over {world_size} GPUs, " + ("NCCL all-gather / all-reduce per order"
+                       if os.environ.get("PAS_EXCHANGE") == "nccl" else
+                       "density slabs stored to all ranks by the kernel over NVLink peer memory, flag barriers")),
                    "l2": "no flush between steps: every step recomputes and rewrites all tables "
                          "(5 x 60 MiB intermediates + products > 126 MB L2), nothing is reused across steps"},
         "e2e": {"value": round(e2e_ms, 4), "unit": "ms", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

@@ -269,6 +269,17 @@ pas_status pas_model_attach_world(pas_model* model, int rank, int world_size,
  * exists, later models attach with nccl_unique_id_bytes == NULL. device = CUDA ordinal. */
 int pas_world_is_cached(int device, int rank, int world_size);
 
+/* Peer-memory exchange (preferred on one NVLink / NVSwitch box): instead of NCCL collectives, the
+ * scattering-density kernel stores its r-slab straight into the tables of the other ranks, the
+ * irradiance partial sums and the final scattering slabs are pushed the same way, and ranks meet at
+ * flag barriers in device memory. Protocol, on every rank: pas_model_ipc_export fills
+ * PAS_IPC_EXPORT_BYTES (CUDA IPC handles of the model's exchange buffers); the host all-gathers
+ * them in rank order (any transport); pas_model_attach_peers maps the others' buffers. Ranks must
+ * be separate processes on GPUs with peer access. No NCCL communicator is needed or created. */
+#define PAS_IPC_EXPORT_BYTES 464
+pas_status pas_model_ipc_export(pas_model* model, int rank, int world_size, void* out, size_t* bytes);
+pas_status pas_model_attach_peers(pas_model* model, const void* all_exports, size_t bytes_per_rank);
+
 /* Device memory of destroyed models is kept in a process-wide pool for the next pas_model_create
  * (the demo re-creates its Model on every settings change, atmosphere/demo/demo.cc:446-494);
  * this returns it to the driver. */

@@ -316,15 +316,17 @@ __device__ __forceinline__ void direction2(float2 (&acc)[NP], const float2* __re
   }
 }
 
-template <int NC, bool ORDER2, int NUM>
+// CP: channel pitch of the tables (4, 8 or 16 floats per texel; nc <= CP channels are live, the rest
+// stay zero). MIRROR: multi-GPU instantiation with the transposed output path.
+template <int CP, bool ORDER2, int NUM, bool MIRROR>
 __global__ void __launch_bounds__(256, 2)
-density_kernel_x2(const __grid_constant__ PasGeometry g, const PasDensityDir* __restrict__ dirs,
+density_kernel_x2(const __grid_constant__ PasGeometry g, int NC, const PasDensityDir* __restrict__ dirs,
                   const float* __restrict__ G, const float* __restrict__ cRk,
                   const float* __restrict__ cMk, const float* __restrict__ tabA,
                   const float* __restrict__ tabB, const float* __restrict__ dE,
-                  float* __restrict__ dJ, int k_begin) {
+                  float* __restrict__ dJ, const __grid_constant__ PeerTables mirrors, int k_begin) {
   constexpr int NT = ORDER2 ? 2 : 1;
-  constexpr int CP = PAS_CHANNEL_PITCH(NC), NP = CP / 2;
+  constexpr int NP = CP / 2;
   extern __shared__ __align__(16) float smem_dyn[];
   __shared__ __align__(16) float2 sA[NT][PAS_DIR_THETA][NP][NUM];
   __shared__ float2 sG[PAS_DIR_THETA][NP];
@@ -498,44 +500,82 @@ density_kernel_x2(const __grid_constant__ PasGeometry g, const PasDensityDir* __
     }
   }
 
-  // one interleaved texel per thread: CP contiguous floats, padding channels zero
-  float4* out = reinterpret_cast<float4*>(dJ + (layer + (size_t)j * width + i_nu * mu_s_n + i_mu_s) * CP);
+  // ---- output: one interleaved texel (CP floats) per thread ---------------------------------------
+  // The texels of a block are 2 KB apart in the table (same column, consecutive (mu, nu)). Each warp
+  // transposes its 32 texels through shared memory so that Q = CP / 4 neighbouring lanes store the
+  // 16-byte vectors of ONE texel: a warp store then covers 32 / Q whole texels instead of 32 isolated
+  // 16-byte pieces. This matters for the copies sent to the other GPUs (multi-GPU: every rank needs
+  // this layer for its multiple-scattering rays): posted stores over NVLink travel as
+  // 64-byte instead of 16-byte packets. They are completed by the barrier kernel that follows.
+  constexpr int Q = CP / 4;
+  if (!MIRROR || Q == 1) {
+    const size_t offset = (layer + (size_t)j * width + i_nu * mu_s_n + i_mu_s) * CP;
 #pragma unroll
-  for (int q = 0; q < CP / 4; ++q) {
-    out[q] = make_float4(acc[2 * q].x, acc[2 * q].y, acc[2 * q + 1].x, acc[2 * q + 1].y);
+    for (int q = 0; q < Q; ++q) {
+      const float4 v = make_float4(acc[2 * q].x, acc[2 * q].y, acc[2 * q + 1].x, acc[2 * q + 1].y);
+      reinterpret_cast<float4*>(dJ + offset)[q] = v;
+      if (MIRROR) {
+        for (int p = 0; p < mirrors.n; ++p) reinterpret_cast<float4*>(mirrors.tab[p] + offset)[q] = v;
+      }
+    }
+    return;
+  }
+  const int lane = tid & 31, warp = tid >> 5;
+  // lanes of this warp that own a texel (the others returned before the direction loop)
+  const int n_live = min(32, mu_n * nu_n - (int)(blockIdx.x * blockDim.x + warp * 32));
+  const unsigned live = n_live >= 32 ? 0xffffffffu : ((1u << n_live) - 1u);
+  float4* stage = reinterpret_cast<float4*>(sDE + NP * e_pad) + warp * 32 * (Q + 1);  // [32][Q + 1]
+#pragma unroll
+  for (int q = 0; q < Q; ++q) {
+    stage[lane * (Q + 1) + q] = make_float4(acc[2 * q].x, acc[2 * q].y, acc[2 * q + 1].x, acc[2 * q + 1].y);
+  }
+  __syncwarp(live);
+#pragma unroll
+  for (int it = 0; it < Q; ++it) {
+    const int idx = it * 32 + lane;
+    const int t = idx / Q, q = idx % Q;      // texel of lane t of this warp, vector q
+    if (!((live >> t) & 1u)) continue;
+    const int tex = blockIdx.x * blockDim.x + warp * 32 + t;
+    const size_t offset = (layer + (size_t)(tex / nu_n) * width + (tex % nu_n) * mu_s_n + i_mu_s) * CP + 4 * q;
+    const float4 v = stage[t * (Q + 1) + q];
+    *reinterpret_cast<float4*>(dJ + offset) = v;
+    for (int p = 0; p < mirrors.n; ++p) *reinterpret_cast<float4*>(mirrors.tab[p] + offset) = v;
   }
 }
 
-template <int NC, bool ORDER2, int NUM>
-cudaError_t launch_one(const PasGeometry& g, const PasDensityDir* dirs, const float* G,
+template <int CP, bool ORDER2, int NUM, bool MIRROR>
+cudaError_t launch_one(const PasGeometry& g, int nc, const PasDensityDir* dirs, const float* G,
                        const float* cR, const float* cM, const float* tabA, const float* tabB,
-                       const float* dE, float* dJ, int k_begin, int k_end, cudaStream_t stream) {
+                       const float* dE, float* dJ, const PeerTables& mirrors, int k_begin, int k_end,
+                       cudaStream_t stream) {
   const int threads = 256;
   const int texels = g.sz.mu_n * g.sz.nu_n;
   dim3 grid((texels + threads - 1) / threads, g.sz.mu_s_n, k_end - k_begin);
-  constexpr int CP = PAS_CHANNEL_PITCH(NC);
-  const size_t dyn = (size_t)2 * CP * (g.sz.e_w + kNG + 1) * sizeof(float);
-  auto kern = density_kernel_x2<NC, ORDER2, NUM>;
+  constexpr int Q = CP / 4;
+  // irradiance row + differences, then (MIRROR) the per-warp output staging [8 warps][32][Q + 1] float4
+  const size_t dyn = (size_t)2 * CP * (g.sz.e_w + kNG + 1) * sizeof(float) +
+                     (MIRROR && Q > 1 ? (size_t)(threads / 32) * 32 * (Q + 1) * sizeof(float4) : 0);
+  auto kern = density_kernel_x2<CP, ORDER2, NUM, MIRROR>;
   if (dyn > 16 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
     if (e != cudaSuccess) return e;
   }
-  kern<<<grid, threads, dyn, stream>>>(g, dirs, G, cR, cM, tabA, tabB, dE, dJ, k_begin);
+  kern<<<grid, threads, dyn, stream>>>(g, nc, dirs, G, cR, cM, tabA, tabB, dE, dJ, mirrors, k_begin);
   return cudaGetLastError();
 }
 
-template <int NC>
-cudaError_t launch_nc(const PasGeometry& g, const PasDensityDir* dirs, const float* G,
+template <int CP, bool MIRROR>
+cudaError_t launch_cp(const PasGeometry& g, int nc, const PasDensityDir* dirs, const float* G,
                       const float* cR, const float* cM, const float* dR, const float* dM,
-                      const float* dS, const float* dE, int order, float* dJ, int k_begin,
-                      int k_end, cudaStream_t stream) {
+                      const float* dS, const float* dE, int order, float* dJ,
+                      const PeerTables& mirrors, int k_begin, int k_end, cudaStream_t stream) {
   const bool wide = g.sz.nu_n > 8;
   if (order == 2) {
-    return wide ? launch_one<NC, true, 16>(g, dirs, G, cR, cM, dR, dM, dE, dJ, k_begin, k_end, stream)
-                : launch_one<NC, true, 8>(g, dirs, G, cR, cM, dR, dM, dE, dJ, k_begin, k_end, stream);
+    return wide ? launch_one<CP, true, 16, MIRROR>(g, nc, dirs, G, cR, cM, dR, dM, dE, dJ, mirrors, k_begin, k_end, stream)
+                : launch_one<CP, true, 8, MIRROR>(g, nc, dirs, G, cR, cM, dR, dM, dE, dJ, mirrors, k_begin, k_end, stream);
   }
-  return wide ? launch_one<NC, false, 16>(g, dirs, G, cR, cM, dS, nullptr, dE, dJ, k_begin, k_end, stream)
-              : launch_one<NC, false, 8>(g, dirs, G, cR, cM, dS, nullptr, dE, dJ, k_begin, k_end, stream);
+  return wide ? launch_one<CP, false, 16, MIRROR>(g, nc, dirs, G, cR, cM, dS, nullptr, dE, dJ, mirrors, k_begin, k_end, stream)
+              : launch_one<CP, false, 8, MIRROR>(g, nc, dirs, G, cR, cM, dS, nullptr, dE, dJ, mirrors, k_begin, k_end, stream);
 }
 
 }  // namespace
@@ -544,12 +584,19 @@ cudaError_t launch_scattering_density(const PasGeometry& g, const PasSpectrum& s
                                       const PasDensityDir* dirs, const float* G, const float* cR,
                                       const float* cM, const float* dR, const float* dM,
                                       const float* dS, const float* dE, int order, float* dJ,
-                                      int k_begin, int k_end, cudaStream_t stream) {
+                                      const PeerTables& mirrors, int k_begin, int k_end,
+                                      cudaStream_t stream) {
   if (g.sz.nu_n < 2 || g.sz.nu_n > PAS_MAX_NU) return cudaErrorInvalidValue;
-  switch (s.nc) {
-#define PAS_CASE(N) \
-  case N: return launch_nc<N>(g, dirs, G, cR, cM, dR, dM, dS, dE, order, dJ, k_begin, k_end, stream);
-    PAS_CASE(3) PAS_CASE(4) PAS_CASE(8) PAS_CASE(15) PAS_CASE(16)
+  if (!channel_count_supported(s.nc)) return cudaErrorInvalidValue;
+  const bool mirror = mirrors.n > 0;
+  switch (PAS_CHANNEL_PITCH(s.nc)) {
+#define PAS_CASE(CP)                                                                                   \
+  case CP:                                                                                             \
+    return mirror ? launch_cp<CP, true>(g, s.nc, dirs, G, cR, cM, dR, dM, dS, dE, order, dJ, mirrors,  \
+                                        k_begin, k_end, stream)                                        \
+                  : launch_cp<CP, false>(g, s.nc, dirs, G, cR, cM, dR, dM, dS, dE, order, dJ, mirrors, \
+                                         k_begin, k_end, stream);
+    PAS_CASE(4) PAS_CASE(8) PAS_CASE(16)
 #undef PAS_CASE
     default: return cudaErrorInvalidValue;
   }

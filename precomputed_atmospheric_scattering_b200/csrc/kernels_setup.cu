@@ -18,11 +18,11 @@ __device__ __forceinline__ double warp_sum(double v) {
 // One warp per texel; the 501 trapezoid samples are strided over the lanes.
 __global__ void __launch_bounds__(256)
 transmittance_kernel(const __grid_constant__ PasGeometry g, const __grid_constant__ PasSpectrum s,
-                     float* __restrict__ T) {
-  const int n = g.sz.t_w * g.sz.t_h;
-  const int texel = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+                     float* __restrict__ T, const __grid_constant__ PeerTables mirrors, int j_begin,
+                     int j_end) {
+  const int texel = j_begin * g.sz.t_w + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
   const int lane = threadIdx.x & 31;
-  if (texel >= n) return;
+  if (texel >= j_end * g.sz.t_w) return;
   const int i = texel % g.sz.t_w, j = texel / g.sz.t_w;
   // texel -> (r, mu), functions.glsl:427-447
   const double x_mu = unit_from_coord((i + 0.5) / g.sz.t_w, g.sz.t_w);
@@ -54,6 +54,8 @@ transmittance_kernel(const __grid_constant__ PasGeometry g, const __grid_constan
       t = (float)exp(-tau);
     }
     T[(size_t)texel * cp + lane] = t;
+    // multi-GPU: every rank computes a band of rows and stores it to all the others
+    for (int p = 0; p < mirrors.n; ++p) mirrors.tab[p][(size_t)texel * cp + lane] = t;
   }
 }
 
@@ -189,10 +191,17 @@ cudaError_t launch_planar_to_interleaved(const float* src, size_t n_texels, int 
 
 cudaError_t launch_transmittance(const PasGeometry& g, const PasSpectrum& s, float* T,
                                  cudaStream_t stream) {
-  const int n = g.sz.t_w * g.sz.t_h;
+  return launch_transmittance_rows(g, s, T, PeerTables{}, 0, g.sz.t_h, stream);
+}
+
+cudaError_t launch_transmittance_rows(const PasGeometry& g, const PasSpectrum& s, float* T,
+                                      const PeerTables& mirrors, int j_begin, int j_end,
+                                      cudaStream_t stream) {
+  const int n = g.sz.t_w * (j_end - j_begin);
+  if (n <= 0) return cudaSuccess;
   const int warps_per_block = 8;
   transmittance_kernel<<<(n + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0,
-                         stream>>>(g, s, T);
+                         stream>>>(g, s, T, mirrors, j_begin, j_end);
   return cudaGetLastError();
 }
 

@@ -23,10 +23,23 @@ struct FinalTables {
   int accumulate;          // 0: first channel group overwrites, 1: adds (GL blend, model.cc:1083)
 };
 
+// Multi-GPU: the same table in the memory of the other GPUs of the box (CUDA IPC mappings, NVLink).
+// A pass that is given mirrors stores every texel it produces to each of them as well, at the same
+// offset, so the exchange of the r-slabs rides on the kernel that computes them.
+#define PAS_MAX_PEERS 7
+struct PeerTables {
+  int n;
+  float* tab[PAS_MAX_PEERS];
+};
+
 // T[c][j][i] = transmittance to the top boundary (ComputeTransmittanceToTopAtmosphereBoundaryTexture,
 // functions.glsl:454-463). One warp per texel, 501 samples split across lanes, fp64.
 cudaError_t launch_transmittance(const PasGeometry& g, const PasSpectrum& s, float* T,
                                  cudaStream_t stream);
+// Rows [j_begin, j_end) only, stored to T and to its mirrors (multi-GPU: one band of rows per rank).
+cudaError_t launch_transmittance_rows(const PasGeometry& g, const PasSpectrum& s, float* T,
+                                      const PeerTables& mirrors, int j_begin, int j_end,
+                                      cudaStream_t stream);
 // Packs channels 0..2 of an interleaved transmittance table into the RGBA32F product table.
 cudaError_t launch_pack_rgba(const float* table, int n_texels, int nc, float* rgba,
                              cudaStream_t stream);
@@ -55,12 +68,14 @@ cudaError_t launch_single_scattering(const PasGeometry& g, const PasSpectrum& s,
                                      cudaStream_t stream);
 
 // Scattering density of `order` >= 2 (functions.glsl:1348-1367) for layers [k_begin, k_end).
-// Reads dR, dM (order 2) or dS (order >= 3) and row 0 of dE.
+// Reads dR, dM (order 2) or dS (order >= 3) and row 0 of dE. Every texel is also stored to the
+// `mirrors` of dJ (none on a single GPU).
 cudaError_t launch_scattering_density(const PasGeometry& g, const PasSpectrum& s,
                                       const PasDensityDir* dirs, const float* G, const float* cR,
                                       const float* cM, const float* dR, const float* dM,
                                       const float* dS, const float* dE, int order, float* dJ,
-                                      int k_begin, int k_end, cudaStream_t stream);
+                                      const PeerTables& mirrors, int k_begin, int k_end,
+                                      cudaStream_t stream);
 
 // Indirect irradiance from radiance of `order` (1: dR/dM with phase functions, else dS)
 // (functions.glsl:1573-1586) for rows [j_begin, j_end) + fused E += L.dE (model.cc:176-190)
@@ -76,6 +91,25 @@ cudaError_t launch_indirect_irradiance(const PasGeometry& g, const PasSpectrum& 
 cudaError_t launch_multiple_scattering(const PasGeometry& g, const PasSpectrum& s, const float* T,
                                        const float* dJ, float* dS, FinalTables fin, int k_begin,
                                        int k_end, cudaStream_t stream);
+
+// ---- multi-GPU exchange over peer memory (peer_exchange.cu) ---------------------------------------
+struct PeerFlags {                 // flags[r]: the flag array of rank r (own memory or IPC mapping)
+  int rank, world;
+  unsigned* flags[PAS_MAX_PEERS + 1];
+  int* error;                      // mapped host memory, set when a barrier times out
+};
+struct PeerTargets {               // destinations of a push: the same buffer on every rank
+  int n;
+  void* dst[PAS_MAX_PEERS + 1];
+};
+// Cross-GPU barrier number `epoch` (epochs increase by one per barrier, in step on every rank).
+cudaError_t launch_peer_barrier(const PeerFlags& f, unsigned epoch, cudaStream_t stream);
+// Copies src[offset, offset + bytes) to the same byte range of every target.
+cudaError_t launch_peer_push(const void* src, size_t bytes, size_t offset_bytes, const PeerTargets& t,
+                             cudaStream_t stream);
+// out[i] = sum over ranks r (in rank order) of parts[r * stride + i].
+cudaError_t launch_sum_partials(const float* parts, int world, size_t stride, int n, float* out,
+                                cudaStream_t stream);
 
 // ---- render-time use of the tables (kernel_render.cu) -------------------------------------------
 struct RenderTables {

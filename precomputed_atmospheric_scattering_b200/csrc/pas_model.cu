@@ -232,6 +232,36 @@ CommCache& comm_cache() {
   return *c;
 }
 
+// Peer-memory worlds: per (device, rank, world size) one flag array (the other ranks signal their
+// barrier epochs into it), the epoch counter and the error word of the barrier kernel; plus the
+// IPC mappings already opened by this process (buffers come back from the pool with the same
+// handles, so re-created models find their peers' tables mapped).
+constexpr int kBarrierChannels = 2;   // main stream, side stream: independent barrier sequences
+constexpr int kChannelWords = 16;
+struct PeerWorld {
+  unsigned* flags = nullptr;   // device memory, kBarrierChannels x kChannelWords words, zero at creation
+  int* error_host = nullptr;   // pinned, mapped
+  int* error_dev = nullptr;
+  unsigned epoch[kBarrierChannels] = {0, 0};
+};
+struct PeerCache {
+  std::mutex mu;
+  std::map<std::tuple<int, int, int>, PeerWorld> worlds;
+  std::map<std::string, void*> opened;
+};
+PeerCache& peer_cache() {
+  static PeerCache* c = new PeerCache();
+  return *c;
+}
+
+// What a rank publishes to the others (pas_model_ipc_export).
+struct PasIpcExport {
+  cudaIpcMemHandle_t T, dJ[2], S, M, xE, flags;
+  int has_M;
+  int pad[3];
+};
+static_assert(sizeof(PasIpcExport) == PAS_IPC_EXPORT_BYTES, "PAS_IPC_EXPORT_BYTES");
+
 }  // namespace
 
 struct pas_model {
@@ -266,6 +296,17 @@ struct pas_model {
   // ---- multi-GPU ----
   int rank = 0, world = 1;
   ncclComm_t comm = nullptr;
+  // peer-memory exchange (pas_model_attach_peers): tables of the other ranks, indexed by rank
+  bool peer = false;
+  PeerWorld* pw = nullptr;
+  DeviceBuffer dJ2, xE;            // second density buffer, irradiance partials [2][world][n_e * nc]
+  float* peer_T[PAS_MAX_PEERS + 1] = {};
+  float* peer_dJ[2][PAS_MAX_PEERS + 1] = {};
+  void* peer_S[PAS_MAX_PEERS + 1] = {};
+  void* peer_M[PAS_MAX_PEERS + 1] = {};
+  float* peer_xE[PAS_MAX_PEERS + 1] = {};
+  unsigned* peer_flags[PAS_MAX_PEERS + 1] = {};
+  unsigned exchanges = 0;          // orders exchanged so far: its parity selects dJ / dJ2 and the xE half
 
   size_t n_t() const { return (size_t)geom.sz.t_w * geom.sz.t_h; }
   size_t n_e() const { return (size_t)geom.sz.e_w * geom.sz.e_h; }
@@ -273,6 +314,13 @@ struct pas_model {
   size_t layer_texels() const { return (size_t)geom.sz.nu_n * geom.sz.mu_s_n * geom.sz.mu_n; }
   int total_channels() const { return (int)lambdas.size(); }
   size_t s_texel_bytes() const { return half ? 8 : 16; }
+  int max_nc() const {
+    int n = 0;
+    for (const auto& g : groups) n = std::max(n, g.nc);
+    return n;
+  }
+  size_t xe_stride() const { return n_e() * (size_t)max_nc(); }   // floats per rank slot
+  float* cur_dJ() const { return (peer && (exchanges & 1)) ? dJ2.f() : dJ.f(); }
   void slab(int* k_begin, int* k_end) const {
     // contiguous r-slabs; the first (r_n % world) ranks get one extra layer
     const int base = geom.sz.r_n / world, extra = geom.sz.r_n % world;
@@ -494,12 +542,24 @@ pas_status allocate(pas_model* m) {
 }
 
 // One phase of Precompute (model.cc:1048-1215) for channel group `gi`.
+// Cross-GPU barrier on `stream`; channel 0 belongs to the main stream of Init, 1 to the side stream.
+pas_status peer_barrier(pas_model* m, int channel, cudaStream_t stream) {
+  pas::PeerFlags f{};
+  f.rank = m->rank;
+  f.world = m->world;
+  for (int r = 0; r < m->world; ++r) f.flags[r] = m->peer_flags[r] + channel * kChannelWords;
+  f.error = m->pw->error_dev;
+  PAS_CUDA(pas::launch_peer_barrier(f, ++m->pw->epoch[channel], stream));
+  m->launches += 1;
+  return PAS_OK;
+}
+
 // `stream`: where the phase is enqueued. `ds_in`: the table holding the previous order's multiple
 // scattering (read by the density and irradiance passes); `ds_out`: where the multiple-scattering
 // pass writes. The reference aliases both to one texture (model.cc:897); Init alternates two buffers
 // so that the irradiance pass of order n can overlap the multiple-scattering pass of order n.
 pas_status run_phase(pas_model* m, int gi, int phase, int order, bool accumulate, cudaStream_t stream,
-                     float* ds_in, float* ds_out) {
+                     float* ds_in, float* ds_out, int channel = 0) {
   const PasSpectrum& sp = m->groups[gi];
   const PasGeometry& g = m->geom;
   int k0, k1;
@@ -507,7 +567,21 @@ pas_status run_phase(pas_model* m, int gi, int phase, int order, bool accumulate
   pas::FinalTables fin = final_tables(m, accumulate);
   switch (phase) {
     case 0:
-      PAS_CUDA(pas::launch_transmittance(g, sp, m->T.f(), stream));
+      if (m->peer) {
+        // a band of transmittance rows per rank, stored to every rank; then all meet
+        pas::PeerTables mirrors{};
+        for (int r = 0; r < m->world; ++r) {
+          if (r != m->rank) mirrors.tab[mirrors.n++] = m->peer_T[r];
+        }
+        const int base = g.sz.t_h / m->world, extra = g.sz.t_h % m->world;
+        const int j0 = m->rank * base + std::min(m->rank, extra);
+        const int j1 = j0 + base + (m->rank < extra ? 1 : 0);
+        PAS_CUDA(pas::launch_transmittance_rows(g, sp, m->T.f(), mirrors, j0, j1, stream));
+        pas_status st = peer_barrier(m, channel, stream);
+        if (st != PAS_OK) return st;
+      } else {
+        PAS_CUDA(pas::launch_transmittance(g, sp, m->T.f(), stream));
+      }
       PAS_CUDA(pas::launch_density_setup(g, sp, m->T.f(), static_cast<PasDensityDir*>(m->dirs.p),
                                          m->G.f(), m->cR.f(), m->cM.f(), stream));
       m->launches += 2;
@@ -522,11 +596,21 @@ pas_status run_phase(pas_model* m, int gi, int phase, int order, bool accumulate
       m->launches += 1;
       break;
     case 3:
+    {
+      // peer mode: the kernel stores its slab to every rank (mirrors), into the density buffer of
+      // this order's parity; the barrier comes with the irradiance partial sums (phase 4)
+      pas::PeerTables mirrors{};
+      const int par = (int)(m->exchanges & 1);
+      if (m->peer) {
+        for (int r = 0; r < m->world; ++r) {
+          if (r != m->rank) mirrors.tab[mirrors.n++] = m->peer_dJ[par][r];
+        }
+      }
       PAS_CUDA(pas::launch_scattering_density(
           g, sp, static_cast<const PasDensityDir*>(m->dirs.p), m->G.f(), m->cR.f(), m->cM.f(),
-          m->dR.f(), m->dM.f(), ds_in, m->dE.f(), order, m->dJ.f(), k0, k1, stream));
+          m->dR.f(), m->dM.f(), ds_in, m->dE.f(), order, m->cur_dJ(), mirrors, k0, k1, stream));
       m->launches += 1;
-      if (m->world > 1) {
+      if (m->world > 1 && !m->peer) {
         // all-gather of the density r-slabs over NVLink: every rank needs every layer its rays
         // cross in the multiple-scattering pass
         // interleaved layout: one layer holds every channel, so each rank's slab is one
@@ -540,8 +624,37 @@ pas_status run_phase(pas_model* m, int gi, int phase, int order, bool accumulate
                                   m->comm, stream));
       }
       break;
+    }
     case 4: {
       if (m->world > 1) fin.irradiance = nullptr;  // partial sums: accumulate after the all-reduce
+      if (m->peer) {
+        // partial sums of this rank's layers go to slot [parity][rank] of every rank's xE; the
+        // barrier that follows also completes the density slabs stored by phase 3
+        const int par = (int)(m->exchanges & 1);
+        const size_t stride = m->xe_stride();
+        const size_t slot = ((size_t)par * m->world + m->rank) * stride;
+        PAS_CUDA(pas::launch_indirect_irradiance(g, sp, m->dR.f(), m->dM.f(), ds_in, order,
+                                                 m->xE.f() + slot, fin, 0, g.sz.e_h, k0, k1, stream));
+        pas::PeerTargets t{};
+        for (int r = 0; r < m->world; ++r) {
+          if (r != m->rank) t.dst[t.n++] = m->peer_xE[r];
+        }
+        PAS_CUDA(pas::launch_peer_push(m->xE.f(), m->n_e() * sp.nc * sizeof(float), slot * sizeof(float), t, stream));
+        if (channel != 0) {
+          // the density slabs stored by phase 3 are completed by a barrier of the main stream
+          pas_status st = peer_barrier(m, 0, m->stream);
+          if (st != PAS_OK) return st;
+        }
+        pas_status st = peer_barrier(m, channel, stream);
+        if (st != PAS_OK) return st;
+        PAS_CUDA(pas::launch_sum_partials(m->xE.f() + (size_t)par * m->world * stride, m->world, stride,
+                                          (int)(m->n_e() * sp.nc), m->dE.f(), stream));
+        const int n = (int)m->n_e();
+        accumulate_irradiance_kernel<<<(n + 127) / 128, 128, 0, stream>>>(m->dE.f(), n, sp.nc, sp, m->E.f());
+        PAS_CUDA(cudaGetLastError());
+        m->launches += 4;
+        break;
+      }
       PAS_CUDA(pas::launch_indirect_irradiance(g, sp, m->dR.f(), m->dM.f(), ds_in, order,
                                                m->dE.f(), fin, 0, g.sz.e_h, k0, k1, stream));
       m->launches += 1;
@@ -557,9 +670,10 @@ pas_status run_phase(pas_model* m, int gi, int phase, int order, bool accumulate
       break;
     }
     case 5:
-      PAS_CUDA(pas::launch_multiple_scattering(g, sp, m->T.f(), m->dJ.f(), ds_out, fin, k0, k1,
+      PAS_CUDA(pas::launch_multiple_scattering(g, sp, m->T.f(), m->cur_dJ(), ds_out, fin, k0, k1,
                                                stream));
       m->launches += 1;
+      if (m->peer) m->exchanges += 1;  // the next order uses the other density buffer / xE half
       break;
     default:
       return fail(PAS_ERR_INVALID_ARGUMENT, "unknown phase");
@@ -723,7 +837,7 @@ pas_status pas_model_init(pas_model* m, unsigned int num_scattering_orders) {
   // of order n; so does the final RGB transmittance, beside everything. With captures (tests) or in
   // a multi-GPU world every pass is enqueued on the one stream, in the reference's order.
   static const bool no_overlap = getenv("PAS_NO_OVERLAP") != nullptr;
-  const bool overlap = !m->capture && m->world == 1 && !no_overlap;
+  const bool overlap = !m->capture && (m->world == 1 || m->peer) && !no_overlap;
   cudaStream_t main = m->stream, side = overlap ? m->aux : m->stream;
   auto side_after_main = [&]() -> cudaError_t {
     if (!overlap) return cudaSuccess;
@@ -770,13 +884,14 @@ pas_status pas_model_init(pas_model* m, unsigned int num_scattering_orders) {
       PAS_CUDA(main_after_side());
       if ((st = run_phase(m, (int)gi, 3, (int)order, blend, main, ds_in, ds_out)) != PAS_OK) return st;
       timer.mark("scattering_density_" + tag);
-      if ((st = capture_copy(m, "delta_density_" + tag, m->dJ.f(), m->n_s(), nc, off, true)) != PAS_OK) return st;
       // irradiance from the radiance of the previous order (model.cc:1187-1188); it overwrites the
       // irradiance table the density pass has just read
       PAS_CUDA(side_after_main());
-      if ((st = run_phase(m, (int)gi, 4, (int)order - 1, blend, side, ds_in, ds_out)) != PAS_OK) return st;
+      if ((st = run_phase(m, (int)gi, 4, (int)order - 1, blend, side, ds_in, ds_out, overlap ? 1 : 0)) != PAS_OK) return st;
       if (!overlap) timer.mark("indirect_irradiance_" + tag);
       if ((st = capture_copy(m, "delta_irradiance_" + tag, m->dE.f(), m->n_e(), nc, off, false)) != PAS_OK) return st;
+      // (multi-GPU: the density table is complete once the exchange of phase 3 / 4 is done)
+      if ((st = capture_copy(m, "delta_density_" + tag, m->cur_dJ(), m->n_s(), nc, off, true)) != PAS_OK) return st;
       if ((st = run_phase(m, (int)gi, 5, (int)order, blend, main, ds_in, ds_out)) != PAS_OK) return st;
       timer.mark("multiple_scattering_" + tag);
       if ((st = capture_copy(m, "delta_multiple_" + tag, ds_out, m->n_s(), nc, off, true)) != PAS_OK) return st;
@@ -789,7 +904,25 @@ pas_status pas_model_init(pas_model* m, unsigned int num_scattering_orders) {
     PAS_CUDA(pas::launch_pack_rgba(m->T.f(), (int)m->n_t(), 3, m->T_rgba.f(), main));
     m->launches += 1;
   }
-  if (m->world > 1) {
+  if (m->world > 1 && m->peer) {
+    // every rank ends with the complete scattering table(s): push this rank's slab, then barrier
+    int k0, k1;
+    m->slab(&k0, &k1);
+    const size_t layer_bytes = m->layer_texels() * m->s_texel_bytes();
+    pas::PeerTargets ts{}, tm{};
+    for (int r = 0; r < m->world; ++r) {
+      if (r == m->rank) continue;
+      ts.dst[ts.n++] = m->peer_S[r];
+      tm.dst[tm.n++] = m->peer_M[r];
+    }
+    PAS_CUDA(pas::launch_peer_push(m->S.p, (size_t)(k1 - k0) * layer_bytes, (size_t)k0 * layer_bytes, ts, main));
+    if (!m->combined) {
+      PAS_CUDA(pas::launch_peer_push(m->M.p, (size_t)(k1 - k0) * layer_bytes, (size_t)k0 * layer_bytes, tm, main));
+    }
+    pas_status st = peer_barrier(m, 0, main);
+    if (st != PAS_OK) return st;
+    m->launches += m->combined ? 1 : 2;
+  } else if (m->world > 1) {
     // every rank ends with the complete scattering table(s)
     int k0, k1;
     m->slab(&k0, &k1);
@@ -806,6 +939,10 @@ pas_status pas_model_init(pas_model* m, unsigned int num_scattering_orders) {
   timer.mark("finalize");
   PAS_CUDA(cudaStreamSynchronize(m->stream));
   timer.finish();
+  if (m->peer && *m->pw->error_host != 0) {
+    *m->pw->error_host = 0;
+    return fail(PAS_ERR_NCCL, "peer barrier timed out: another rank failed or is out of step");
+  }
   m->initialised = true;
   return PAS_OK;
 }
@@ -1083,6 +1220,115 @@ pas_status pas_model_attach_world(pas_model* m, int rank, int world_size, const 
   }
   m->rank = rank;
   m->world = world_size;
+  return PAS_OK;
+}
+
+pas_status pas_model_ipc_export(pas_model* m, int rank, int world_size, void* out, size_t* bytes) {
+  if (m == nullptr || bytes == nullptr) return fail(PAS_ERR_INVALID_ARGUMENT, "NULL argument");
+  if (out == nullptr || *bytes < sizeof(PasIpcExport)) {
+    *bytes = sizeof(PasIpcExport);
+    return out == nullptr ? PAS_OK : fail(PAS_ERR_INVALID_ARGUMENT, "export buffer too small");
+  }
+  if (world_size < 2 || world_size > PAS_MAX_PEERS + 1 || rank < 0 || rank >= world_size) {
+    return fail(PAS_ERR_INVALID_ARGUMENT, "peer worlds have 2..8 ranks");
+  }
+  if (m->geom.sz.r_n % world_size != 0) {
+    return fail(PAS_ERR_UNSUPPORTED, "scattering_r must be divisible by the world size");
+  }
+  PAS_CUDA(cudaSetDevice(m->device));
+  m->rank = rank;
+  m->world = world_size;
+  const size_t cp = PAS_CHANNEL_PITCH(m->max_nc());
+  PAS_CUDA(m->dJ2.ensure(m->n_s() * cp * sizeof(float)));
+  PAS_CUDA(m->xE.ensure((size_t)2 * world_size * m->xe_stride() * sizeof(float)));
+  if (!m->combined) PAS_CUDA(m->M.ensure(m->n_s() * m->s_texel_bytes()));
+  {
+    PeerCache& cache = peer_cache();
+    std::lock_guard<std::mutex> lock(cache.mu);
+    PeerWorld& w = cache.worlds[std::make_tuple(m->device, rank, world_size)];
+    if (w.flags == nullptr) {
+      PAS_CUDA(cudaMalloc(&w.flags, 64 * sizeof(unsigned)));
+      PAS_CUDA(cudaMemset(w.flags, 0, 64 * sizeof(unsigned)));
+      PAS_CUDA(cudaHostAlloc(&w.error_host, sizeof(int), cudaHostAllocMapped));
+      *w.error_host = 0;
+      PAS_CUDA(cudaHostGetDevicePointer(&w.error_dev, w.error_host, 0));
+      PAS_CUDA(cudaDeviceSynchronize());
+      w.epoch[0] = w.epoch[1] = 0;
+    }
+    m->pw = &w;
+  }
+  PasIpcExport e{};
+  PAS_CUDA(cudaIpcGetMemHandle(&e.T, m->T.p));
+  PAS_CUDA(cudaIpcGetMemHandle(&e.dJ[0], m->dJ.p));
+  PAS_CUDA(cudaIpcGetMemHandle(&e.dJ[1], m->dJ2.p));
+  PAS_CUDA(cudaIpcGetMemHandle(&e.S, m->S.p));
+  e.has_M = m->combined ? 0 : 1;
+  if (e.has_M) PAS_CUDA(cudaIpcGetMemHandle(&e.M, m->M.p));
+  PAS_CUDA(cudaIpcGetMemHandle(&e.xE, m->xE.p));
+  PAS_CUDA(cudaIpcGetMemHandle(&e.flags, m->pw->flags));
+  std::memcpy(out, &e, sizeof e);
+  *bytes = sizeof e;
+  return PAS_OK;
+}
+
+namespace {
+pas_status open_peer(const cudaIpcMemHandle_t& h, void** ptr) {
+  PeerCache& cache = peer_cache();
+  std::lock_guard<std::mutex> lock(cache.mu);
+  const std::string key(reinterpret_cast<const char*>(&h), sizeof h);
+  auto it = cache.opened.find(key);
+  if (it != cache.opened.end()) {
+    *ptr = it->second;
+    return PAS_OK;
+  }
+  PAS_CUDA(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  cache.opened[key] = *ptr;
+  return PAS_OK;
+}
+}  // namespace
+
+pas_status pas_model_attach_peers(pas_model* m, const void* exports, size_t bytes_per_rank) {
+  if (m == nullptr || exports == nullptr) return fail(PAS_ERR_INVALID_ARGUMENT, "NULL argument");
+  if (m->pw == nullptr || m->world < 2) {
+    return fail(PAS_ERR_INVALID_ARGUMENT, "call pas_model_ipc_export first");
+  }
+  if (bytes_per_rank != sizeof(PasIpcExport)) return fail(PAS_ERR_INVALID_ARGUMENT, "bad export size");
+  PAS_CUDA(cudaSetDevice(m->device));
+  for (int r = 0; r < m->world; ++r) {
+    PasIpcExport e;
+    std::memcpy(&e, static_cast<const char*>(exports) + (size_t)r * bytes_per_rank, sizeof e);
+    if (r == m->rank) {
+      m->peer_T[r] = m->T.f();
+      m->peer_dJ[0][r] = m->dJ.f();
+      m->peer_dJ[1][r] = m->dJ2.f();
+      m->peer_S[r] = m->S.p;
+      m->peer_M[r] = m->M.p;
+      m->peer_xE[r] = m->xE.f();
+      m->peer_flags[r] = m->pw->flags;
+      continue;
+    }
+    if ((e.has_M != 0) == m->combined) return fail(PAS_ERR_INVALID_ARGUMENT, "ranks disagree on the model");
+    pas_status st;
+    void* p = nullptr;
+    if ((st = open_peer(e.T, &p)) != PAS_OK) return st;
+    m->peer_T[r] = static_cast<float*>(p);
+    if ((st = open_peer(e.dJ[0], &p)) != PAS_OK) return st;
+    m->peer_dJ[0][r] = static_cast<float*>(p);
+    if ((st = open_peer(e.dJ[1], &p)) != PAS_OK) return st;
+    m->peer_dJ[1][r] = static_cast<float*>(p);
+    if ((st = open_peer(e.S, &p)) != PAS_OK) return st;
+    m->peer_S[r] = p;
+    if (e.has_M) {
+      if ((st = open_peer(e.M, &p)) != PAS_OK) return st;
+      m->peer_M[r] = p;
+    }
+    if ((st = open_peer(e.xE, &p)) != PAS_OK) return st;
+    m->peer_xE[r] = static_cast<float*>(p);
+    if ((st = open_peer(e.flags, &p)) != PAS_OK) return st;
+    m->peer_flags[r] = static_cast<unsigned*>(p);
+  }
+  m->peer = true;
+  m->exchanges = 0;
   return PAS_OK;
 }
 

@@ -1,0 +1,92 @@
+// Multi-GPU exchange over peer memory (one process per GPU, CUDA IPC mappings of the other ranks'
+// tables, NVLink / NVSwitch underneath): no collective library call on the data path.
+//
+//   * the scattering-density kernel stores every texel it computes to all ranks (kernel_density.cu):
+//     the all-gather of SURVEY.md section 8e is fused into the pass that produces the data;
+//   * peer_push: a rank's irradiance partial sums (60 KiB) and, at the end of Init, its slab of the
+//     final scattering table(s) are copied to the same offset of every rank's buffer;
+//   * peer_barrier: every rank writes the epoch number into its slot of every other rank's flag
+//     array (release, system scope) and waits until all the slots of its own array have reached it.
+//     Stream order + the fence make the stores of the kernels enqueued before the barrier visible
+//     to the kernels every rank enqueues after it.
+//   * sum_partials: irradiance = sum over ranks of the partial sums, in rank order on every rank
+//     (bit-identical results everywhere).
+#include "pas_kernels.h"
+
+namespace pas {
+namespace {
+
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
+__global__ void peer_barrier_kernel(PeerFlags f, unsigned epoch, unsigned long long timeout_ns) {
+  const int p = threadIdx.x;
+  if (p >= f.world || p == f.rank) return;
+  __threadfence_system();
+  unsigned* dst = f.flags[p] + f.rank;
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(dst), "r"(epoch) : "memory");
+  const unsigned* src = f.flags[f.rank] + p;
+  const unsigned long long t0 = global_timer_ns();
+  for (;;) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(src) : "memory");
+    if ((int)(v - epoch) >= 0) break;
+    if (global_timer_ns() - t0 > timeout_ns) {
+      *f.error = 1;  // mapped host memory: a rank died or fell out of step; Init reports it
+      break;
+    }
+    __nanosleep(200);
+  }
+  __threadfence_system();
+}
+
+template <typename V>
+__global__ void peer_push_kernel(const V* __restrict__ src, size_t n, size_t offset, PeerTargets t) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const V v = src[offset + i];
+    for (int p = 0; p < t.n; ++p) reinterpret_cast<V*>(t.dst[p])[offset + i] = v;
+  }
+}
+
+__global__ void sum_partials_kernel(const float* __restrict__ parts, int world, size_t stride, int n,
+                                    float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float s = 0.f;
+  for (int r = 0; r < world; ++r) s += parts[(size_t)r * stride + i];
+  out[i] = s;
+}
+
+}  // namespace
+
+cudaError_t launch_peer_barrier(const PeerFlags& f, unsigned epoch, cudaStream_t stream) {
+  peer_barrier_kernel<<<1, 32, 0, stream>>>(f, epoch, 5000000000ull);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_peer_push(const void* src, size_t bytes, size_t offset_bytes, const PeerTargets& t,
+                             cudaStream_t stream) {
+  if (bytes == 0 || t.n == 0) return cudaSuccess;
+  if (bytes % 16 == 0 && offset_bytes % 16 == 0) {
+    const size_t n = bytes / 16;
+    const int blocks = (int)((n + 255) / 256 < 592 ? (n + 255) / 256 : 592);
+    peer_push_kernel<uint4><<<blocks, 256, 0, stream>>>(static_cast<const uint4*>(src), n, offset_bytes / 16, t);
+  } else {
+    if (bytes % 4 != 0 || offset_bytes % 4 != 0) return cudaErrorInvalidValue;
+    const size_t n = bytes / 4;
+    const int blocks = (int)((n + 255) / 256 < 592 ? (n + 255) / 256 : 592);
+    peer_push_kernel<float><<<blocks, 256, 0, stream>>>(static_cast<const float*>(src), n, offset_bytes / 4, t);
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_sum_partials(const float* parts, int world, size_t stride, int n, float* out,
+                                cudaStream_t stream) {
+  sum_partials_kernel<<<(n + 255) / 256, 256, 0, stream>>>(parts, world, stride, n, out);
+  return cudaGetLastError();
+}
+
+}  // namespace pas

@@ -78,6 +78,9 @@ class _TextureInfo(ctypes.Structure):
 _lib = None
 
 
+IPC_EXPORT_BYTES = 464  # PAS_IPC_EXPORT_BYTES
+
+
 def load_library() -> ctypes.CDLL:
     """Loads the in-tree C-ABI library. Fails loudly if it has not been built."""
     global _lib
@@ -110,6 +113,8 @@ def load_library() -> ctypes.CDLL:
         lib.pas_nccl_unique_id.argtypes = [ctypes.c_void_p]
         lib.pas_model_attach_world.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
         lib.pas_world_is_cached.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int]
+        lib.pas_model_ipc_export.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.POINTER(ctypes.c_size_t)]
+        lib.pas_model_attach_peers.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]
         lib.pas_release_cached_memory.restype = None
         _FP = ctypes.POINTER(ctypes.c_float)
         lib.pas_model_get_solar_radiance.argtypes = [ctypes.c_void_p, ctypes.c_int, _DP]
@@ -450,3 +455,15 @@ class Model:
 
     def attach_world(self, rank: int, world_size: int, unique_id: Optional[bytes]) -> None:
         _check(self._lib.pas_model_attach_world(self._h, rank, world_size, unique_id))
+
+    def ipc_export(self, rank: int, world_size: int) -> bytes:
+        """CUDA IPC handles of this rank's exchange buffers (pas_model_ipc_export), to be
+        all-gathered by the host and handed to ``attach_peers`` on every rank."""
+        n = ctypes.c_size_t(IPC_EXPORT_BYTES)
+        buf = ctypes.create_string_buffer(IPC_EXPORT_BYTES)
+        _check(self._lib.pas_model_ipc_export(self._h, rank, world_size, buf, ctypes.byref(n)))
+        return buf.raw[:n.value]
+
+    def attach_peers(self, exports: bytes, bytes_per_rank: int = 0) -> None:
+        """Maps the other ranks' buffers: ``exports`` = the ranks' ``ipc_export`` blobs in rank order."""
+        _check(self._lib.pas_model_attach_peers(self._h, exports, bytes_per_rank or IPC_EXPORT_BYTES))

@@ -1,13 +1,18 @@
 """Multi-GPU plumbing: one process per GPU, rendezvous through ``torch.distributed``.
 
-The compute and the NVLink exchange live in libpas_b200.so (r-slab sharding of every 3-D pass, NCCL
-all-gather of the scattering-density slabs and all-reduce of the irradiance partial sums between
-orders, see include/pas_b200.h ``pas_model_attach_world``). What is left for the host is to agree
-on an NCCL unique id and on who owns which r-layers; that is all this module does. It works with
-any torch.distributed backend (``nccl`` on the GPU box, ``gloo`` in the CPU tests).
+The compute and the NVLink exchange live in libpas_b200.so (r-slab sharding of every 3-D pass). Two
+exchanges are built (include/pas_b200.h):
+  * ``peer`` (default): the scattering-density kernel stores its r-slab straight into the other
+    ranks' tables (CUDA IPC mappings), irradiance partial sums and final slabs are pushed the same
+    way, ranks meet at flag barriers in device memory -- no collective library on the data path;
+  * ``nccl``: all-gather of the density slabs / all-reduce of the irradiance partial sums.
+What is left for the host is to move a few hundred bytes once per model -- the ranks' IPC handles
+(or an NCCL unique id) -- and to agree on who owns which r-layers; that is all this module does. It
+works with any torch.distributed backend (``nccl`` on the GPU box, ``gloo`` in the CPU tests).
 """
 from __future__ import annotations
 
+import os
 from typing import Callable, List, Optional, Tuple
 
 import torch
@@ -52,13 +57,36 @@ def broadcast_unique_id(make_id: Callable[[], bytes], group=None, device: Option
     return bytes(buf.cpu().tolist())
 
 
-def attach(model, group=None) -> Tuple[int, int]:
-    """Attaches ``model`` (model.Model) to the default process group: returns (rank, world)."""
+def _host_device(group) -> torch.device:
+    return torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" \
+        else torch.device("cpu")
+
+
+def all_gather_bytes(blob: bytes, group=None, device: Optional[torch.device] = None) -> bytes:
+    """Concatenation, in rank order, of every rank's ``blob`` (equal lengths)."""
+    world = dist.get_world_size(group)
+    device = device or _host_device(group)
+    mine = torch.frombuffer(bytearray(blob), dtype=torch.uint8).to(device)
+    parts = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(parts, mine, group=group)
+    return b"".join(bytes(p.cpu().numpy().tobytes()) for p in parts)
+
+
+def attach(model, group=None, exchange: Optional[str] = None) -> Tuple[int, int]:
+    """Attaches ``model`` (model.Model) to the default process group: returns (rank, world).
+    ``exchange``: "peer" (default; env PAS_EXCHANGE overrides) or "nccl"."""
     from .model import nccl_unique_id, world_is_cached
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     if world == 1:
         model.attach_world(0, 1, None)
         return rank, world
+    exchange = exchange or os.environ.get("PAS_EXCHANGE", "peer")
+    if exchange == "peer":
+        blob = model.ipc_export(rank, world)
+        model.attach_peers(all_gather_bytes(blob, group), len(blob))
+        return rank, world
+    if exchange != "nccl":
+        raise ValueError("exchange must be 'peer' or 'nccl'")
     device = model.device if model.device is not None else torch.cuda.current_device()
     # the library keeps one communicator per (device, rank, world) for the life of the process;
     # every rank takes the same branch because every rank has attached the same number of models

@@ -1,7 +1,8 @@
-"""Multi-GPU parity: r-slab sharding over 2 (or more) B200s with the NCCL exchange inside the
-library must give the single-GPU tables bit for bit (same kernels, same per-texel order of
-operations; the all-gather only moves data), except the irradiance, whose per-slab partial sums are
-all-reduced (different summation order, compared at 1e-6). Skipped with fewer than 2 GPUs."""
+"""Multi-GPU parity: r-slab sharding over 2 (or more) B200s with the exchange inside the library --
+peer-memory stores fused into the density kernel + flag barriers, or NCCL collectives -- must give
+the single-GPU tables bit for bit (same kernels, same per-texel order of operations; the exchange
+only moves data), except the irradiance, whose per-slab partial sums are added in a different order
+(compared at 1e-6). Skipped with fewer than 2 GPUs."""
 import os
 import socket
 
@@ -21,7 +22,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world_size, port, out_dir, full_size):
+def _worker(rank, world_size, port, out_dir, full_size, exchange):
     import torch.distributed as dist
 
     import precomputed_atmospheric_scattering_b200 as pas
@@ -35,26 +36,30 @@ def _worker(rank, world_size, port, out_dir, full_size):
         kw = {} if full_size else dict(sizes=SIZES)
         for attempt in range(2):  # the second model re-uses the cached communicator
             model = pas.Model.from_spec(spec, device=rank, **kw)
-            assert world.attach(model) == (rank, world_size)
+            assert world.attach(model, exchange=exchange) == (rank, world_size)
             model.Init(4)
             np.savez(os.path.join(out_dir, f"rank{rank}_{attempt}.npz"), S=model.scattering,
                      E=model.irradiance, T=model.transmittance)
             model.close()
-        assert pas.world_is_cached(rank, rank, world_size)
+        assert pas.world_is_cached(rank, rank, world_size) == (exchange == "nccl")
         dist.barrier()
     finally:
         dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("exchange", ["peer", "nccl"])
 @pytest.mark.parametrize("full_size", [False, True], ids=["small", "earth15"])
 @pytest.mark.timeout(600)
-def test_two_gpus_match_one(tmp_path, pas, full_size):
+def test_two_gpus_match_one(tmp_path, pas, full_size, exchange):
     n = torch.cuda.device_count()
     if n < 2:
         pytest.skip("needs >= 2 GPUs")
-    world_size = 2
+    world_size = int(os.environ.get("PAS_TEST_WORLD", "2"))
+    if n < world_size:
+        pytest.skip(f"needs >= {world_size} GPUs")
     import torch.multiprocessing as mp
-    mp.spawn(_worker, args=(world_size, _free_port(), str(tmp_path), full_size), nprocs=world_size, join=True)
+    mp.spawn(_worker, args=(world_size, _free_port(), str(tmp_path), full_size, exchange), nprocs=world_size,
+             join=True)
     spec = pas.earth(15, half_precision=False) if full_size else pas.small_planet()
     single = pas.Model.from_spec(spec, device=0, **({} if full_size else dict(sizes=SIZES)))
     single.Init(4)

@@ -33,6 +33,9 @@ def _worker(rank, world_size, port, out_dir):
         # 1. every rank ends up with rank 0's unique id
         uid = world.broadcast_unique_id(lambda: bytes(range(128)))
         assert uid == bytes(range(128))
+        # 1b. the IPC-handle exchange of the peer path: every rank gets every blob, in rank order
+        blobs = world.all_gather_bytes(bytes([rank]) * 400)
+        assert blobs == b"".join(bytes([r]) * 400 for r in range(world_size))
         # 2. the slowest rank defines the step time
         assert world.max_over_ranks(10.0 + rank) == 10.0 + world_size - 1
         # 3. r-slab sharded density pass == single-process pass, bit for bit
