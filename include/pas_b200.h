@@ -112,6 +112,13 @@ void pas_model_destroy(pas_model* model);
  * Precompute, :1048-1215): runs every pass on the GPU and returns when the tables are complete in
  * device memory. May be called again (e.g. with another order count). */
 pas_status pas_model_init(pas_model* model, unsigned int num_scattering_orders);
+/* The same work without blocking the host: pas_model_init_async enqueues the whole precomputation on
+ * the model's own streams and returns; pas_model_wait blocks until it is done (pas_model_init is the
+ * two calls back to back). Several models (a batch of atmospheres: turbidity / ozone / albedo
+ * sweeps) can be in flight at once; their kernels share the GPU. Every other call on a model waits
+ * for its Init first. */
+pas_status pas_model_init_async(pas_model* model, unsigned int num_scattering_orders);
+pas_status pas_model_wait(pas_model* model);
 
 pas_status pas_model_texture_info(const pas_model* model, pas_texture which,
                                   pas_texture_info* info);

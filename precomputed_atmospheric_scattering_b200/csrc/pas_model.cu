@@ -264,6 +264,10 @@ static_assert(sizeof(PasIpcExport) == PAS_IPC_EXPORT_BYTES, "PAS_IPC_EXPORT_BYTE
 
 }  // namespace
 
+struct PhaseMarks {
+  std::vector<std::pair<std::string, cudaEvent_t>> marks;
+};
+
 struct pas_model {
   // ---- what the constructor was given (SI units) ----
   std::vector<double> wavelengths, solar, rayleigh, mie_sca, mie_ext, absorption, albedo;
@@ -292,6 +296,8 @@ struct pas_model {
   bool capture = false;
   std::map<std::string, std::unique_ptr<DeviceBuffer>> captured;
   std::vector<std::pair<std::string, float>> timings;
+  PhaseMarks pending;               // events of an Init that has been enqueued but not waited for
+  bool in_flight = false;
   int launches = 0;
   // ---- multi-GPU ----
   int rank = 0, world = 1;
@@ -406,17 +412,22 @@ void split_channels(int total, std::vector<int>* sizes) {
   for (int n = total; n > 0 && pick[n] > 0; n -= pick[n]) sizes->push_back(pick[n]);
 }
 
+struct nullptr_model_tag {};
 struct PhaseTimer {
   pas_model* m;
-  std::vector<std::pair<std::string, cudaEvent_t>> marks;
-  explicit PhaseTimer(pas_model* model) : m(model) {}
+  explicit PhaseTimer(pas_model* model) : m(model) {
+    for (auto& mk : m->pending.marks) cudaEventDestroy(mk.second);
+    m->pending.marks.clear();
+  }
+  PhaseTimer(nullptr_model_tag, pas_model* model) : m(model) {}  // picks up the marks of an Init in flight
   void mark(const std::string& name) {
     cudaEvent_t e;
     if (cudaEventCreate(&e) != cudaSuccess) return;
     cudaEventRecord(e, m->stream);
-    marks.emplace_back(name, e);
+    m->pending.marks.emplace_back(name, e);
   }
   void finish() {
+    auto& marks = m->pending.marks;
     m->timings.clear();
     for (size_t i = 1; i < marks.size(); ++i) {
       float ms = 0.f;
@@ -543,6 +554,11 @@ pas_status allocate(pas_model* m) {
 
 // One phase of Precompute (model.cc:1048-1215) for channel group `gi`.
 // Cross-GPU barrier on `stream`; channel 0 belongs to the main stream of Init, 1 to the side stream.
+// Entry points that read results first wait for an Init still in flight (pas_model_init_async).
+pas_status settle(const pas_model* m) {
+  return (m != nullptr && m->in_flight) ? pas_model_wait(const_cast<pas_model*>(m)) : PAS_OK;
+}
+
 pas_status peer_barrier(pas_model* m, int channel, cudaStream_t stream) {
   pas::PeerFlags f{};
   f.rank = m->rank;
@@ -817,6 +833,7 @@ void pas_model_destroy(pas_model* m) {
   if (m->stream) {
     cudaStreamSynchronize(m->stream);
   }
+  for (auto& mk : m->pending.marks) cudaEventDestroy(mk.second);
   if (m->aux) {
     cudaStreamSynchronize(m->aux);
     cudaStreamDestroy(m->aux);
@@ -828,9 +845,33 @@ void pas_model_destroy(pas_model* m) {
 }
 
 pas_status pas_model_init(pas_model* m, unsigned int num_scattering_orders) {
+  pas_status st = pas_model_init_async(m, num_scattering_orders);
+  return st != PAS_OK ? st : pas_model_wait(m);
+}
+
+pas_status pas_model_wait(pas_model* m) {
+  if (m == nullptr) return fail(PAS_ERR_INVALID_ARGUMENT, "model is NULL");
+  if (!m->in_flight) return PAS_OK;
+  PAS_CUDA(cudaSetDevice(m->device));
+  m->in_flight = false;
+  PAS_CUDA(cudaStreamSynchronize(m->stream));
+  PhaseTimer(nullptr_model_tag(), m).finish();
+  if (m->peer && *m->pw->error_host != 0) {
+    *m->pw->error_host = 0;
+    return fail(PAS_ERR_NCCL, "peer barrier timed out: another rank failed or is out of step");
+  }
+  m->initialised = true;
+  return PAS_OK;
+}
+
+pas_status pas_model_init_async(pas_model* m, unsigned int num_scattering_orders) {
   if (m == nullptr) return fail(PAS_ERR_INVALID_ARGUMENT, "model is NULL");
   if (num_scattering_orders < 1) return fail(PAS_ERR_INVALID_ARGUMENT, "need >= 1 scattering order");
   PAS_CUDA(cudaSetDevice(m->device));
+  if (m->in_flight) {
+    pas_status st = pas_model_wait(m);
+    if (st != PAS_OK) return st;
+  }
   m->launches = 0;
   // Overlapped schedule (single GPU, no captures): the irradiance pass of order n depends on the
   // radiance of order n - 1 only, so it runs on the side stream beside the multiple-scattering pass
@@ -937,13 +978,7 @@ pas_status pas_model_init(pas_model* m, unsigned int num_scattering_orders) {
     PAS_NCCL(nccl().GroupEnd());
   }
   timer.mark("finalize");
-  PAS_CUDA(cudaStreamSynchronize(m->stream));
-  timer.finish();
-  if (m->peer && *m->pw->error_host != 0) {
-    *m->pw->error_host = 0;
-    return fail(PAS_ERR_NCCL, "peer barrier timed out: another rank failed or is out of step");
-  }
-  m->initialised = true;
+  m->in_flight = true;
   return PAS_OK;
 }
 
@@ -953,6 +988,7 @@ pas_status pas_model_texture_info(const pas_model* m, pas_texture which, pas_tex
 }
 
 pas_status pas_model_texture_device_ptr(const pas_model* m, pas_texture which, const void** ptr) {
+  { pas_status settled = settle(m); if (settled != PAS_OK) return settled; }
   if (m == nullptr || ptr == nullptr) return fail(PAS_ERR_INVALID_ARGUMENT, "NULL argument");
   const DeviceBuffer* buf = nullptr;
   pas_texture_info info;
@@ -965,6 +1001,7 @@ pas_status pas_model_texture_device_ptr(const pas_model* m, pas_texture which, c
 
 pas_status pas_model_read_texture(pas_model* m, pas_texture which, int as_float32, void* dst,
                                   size_t dst_bytes) {
+  { pas_status settled = settle(m); if (settled != PAS_OK) return settled; }
   if (m == nullptr || dst == nullptr) return fail(PAS_ERR_INVALID_ARGUMENT, "NULL argument");
   if (!m->initialised) return fail(PAS_ERR_STATE, "pas_model_init has not been called");
   const DeviceBuffer* buf = nullptr;
@@ -994,6 +1031,7 @@ pas_status pas_model_read_texture(pas_model* m, pas_texture which, int as_float3
 }
 
 pas_status pas_model_save_dat(pas_model* m, const char* directory) {
+  { pas_status settled = settle(m); if (settled != PAS_OK) return settled; }
   if (m == nullptr || directory == nullptr) return fail(PAS_ERR_INVALID_ARGUMENT, "NULL argument");
   static const struct { pas_texture id; const char* file; } kFiles[] = {
       {PAS_TEXTURE_TRANSMITTANCE, "transmittance.dat"},
@@ -1081,6 +1119,7 @@ pas_status pas_model_set_capture(pas_model* m, int enabled) {
 }
 
 pas_status pas_model_read_intermediate(pas_model* m, const char* name, float* dst, size_t* num_floats) {
+  { pas_status settled = settle(m); if (settled != PAS_OK) return settled; }
   if (m == nullptr || name == nullptr || num_floats == nullptr) {
     return fail(PAS_ERR_INVALID_ARGUMENT, "NULL argument");
   }
@@ -1120,6 +1159,7 @@ pas_status pas_model_read_intermediate(pas_model* m, const char* name, float* ds
 
 pas_status pas_model_write_intermediate(pas_model* m, const char* name, const float* src,
                                         size_t num_floats) {
+  { pas_status settled = settle(m); if (settled != PAS_OK) return settled; }
   if (m == nullptr || name == nullptr || src == nullptr) return fail(PAS_ERR_INVALID_ARGUMENT, "NULL argument");
   PAS_CUDA(cudaSetDevice(m->device));
   float* live = nullptr;
@@ -1144,6 +1184,7 @@ pas_status pas_model_write_intermediate(pas_model* m, const char* name, const fl
 }
 
 pas_status pas_model_run_phase(pas_model* m, int phase, int order) {
+  { pas_status settled = settle(m); if (settled != PAS_OK) return settled; }
   if (m == nullptr) return fail(PAS_ERR_INVALID_ARGUMENT, "model is NULL");
   if (m->groups.size() != 1) return fail(PAS_ERR_UNSUPPORTED, "single passes need <= 16 channels");
   PAS_CUDA(cudaSetDevice(m->device));
@@ -1154,6 +1195,7 @@ pas_status pas_model_run_phase(pas_model* m, int phase, int order) {
 }
 
 pas_status pas_model_last_timings(const pas_model* m, int* count, const char** names, float* ms) {
+  { pas_status settled = settle(m); if (settled != PAS_OK) return settled; }
   if (m == nullptr || count == nullptr) return fail(PAS_ERR_INVALID_ARGUMENT, "NULL argument");
   const int cap = *count;
   *count = (int)m->timings.size();
@@ -1347,6 +1389,7 @@ bool is_device_pointer(const void* p) {
 }
 
 pas_status render_ready(const pas_model* m, int use_luminance) {
+  { pas_status settled = settle(m); if (settled != PAS_OK) return settled; }
   if (m == nullptr) return fail(PAS_ERR_INVALID_ARGUMENT, "model is NULL");
   if (!m->initialised) return fail(PAS_ERR_STATE, "pas_model_init has not been called");
   if (!use_luminance && m->num_precomputed_wavelengths > 3) {

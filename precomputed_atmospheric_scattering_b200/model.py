@@ -94,6 +94,8 @@ def load_library() -> ctypes.CDLL:
         lib.pas_model_create.argtypes = [ctypes.POINTER(_Params), ctypes.POINTER(ctypes.c_void_p)]
         lib.pas_model_destroy.argtypes = [ctypes.c_void_p]
         lib.pas_model_init.argtypes = [ctypes.c_void_p, ctypes.c_uint]
+        lib.pas_model_init_async.argtypes = [ctypes.c_void_p, ctypes.c_uint]
+        lib.pas_model_wait.argtypes = [ctypes.c_void_p]
         lib.pas_model_texture_info.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(_TextureInfo)]
         lib.pas_model_texture_device_ptr.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]
         lib.pas_model_read_texture.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t]
@@ -268,6 +270,14 @@ class Model:
     def Init(self, num_scattering_orders: int = 4) -> None:
         """atmosphere::Model::Init (atmosphere/model.cc:866-975)."""
         _check(self._lib.pas_model_init(self._h, int(num_scattering_orders)))
+
+    def InitAsync(self, num_scattering_orders: int = 4) -> None:
+        """Enqueues Init on the model's own CUDA streams and returns (pas_model_init_async); several
+        models can be in flight at once. ``Wait`` -- or any call that reads results -- blocks."""
+        _check(self._lib.pas_model_init_async(self._h, int(num_scattering_orders)))
+
+    def Wait(self) -> None:
+        _check(self._lib.pas_model_wait(self._h))
 
     def GetShaderSource(self, glsl_directory: str) -> str:
         """The source atmosphere::Model::shader() compiles (atmosphere/model.cc:691-744, 769-772)."""
