@@ -608,43 +608,83 @@ single_scattering_kernel(const __grid_constant__ PasGeometry g,
   for (int q = 0; q < Q; ++q) accR[q] = accM[q] = make_float4(0.f, 0.f, 0.f, 0.f);
   __syncthreads();
 
+  // Reference row width (WIDTH > 0): the two transmittance rows bracketing r_i live in two register
+  // slots, even rows in A and odd rows in B. A row shared with the previous sample is not read again
+  // (about half of them), and the rows of sample i + 1 are requested right after the staged row of
+  // sample i is written, so that they travel while the block does the sun lookups of sample i.
+  // Bits 16.. of y0 carry the slots to (re)load: 1 = A, 2 = B.
+  if (WIDTH > 0) {
+    int mask = 0;
+    if (tid < kSamples) {
+      const int y0 = sSample[tid].y0, y1 = sSample[tid].y1;
+      const int even = (y0 & 1) == 0 ? y0 : ((y1 & 1) == 0 ? y1 : -1);
+      const int odd = (y0 & 1) == 1 ? y0 : ((y1 & 1) == 1 ? y1 : -1);
+      int p_even = -1, p_odd = -1;
+      if (tid > 0) {
+        const int q0 = sSample[tid - 1].y0, q1 = sSample[tid - 1].y1;
+        p_even = (q0 & 1) == 0 ? q0 : ((q1 & 1) == 0 ? q1 : -1);
+        p_odd = (q0 & 1) == 1 ? q0 : ((q1 & 1) == 1 ? q1 : -1);
+      }
+      mask = (even >= 0 && even != p_even ? 1 : 0) | (odd >= 0 && odd != p_odd ? 2 : 0);
+    }
+    __syncthreads();
+    if (tid < kSamples) sSample[tid].y0 |= mask << 16;
+    __syncthreads();
+  }
+
   if (ray.d_end > 0.0) {
+    float4 A[Q], B[Q];
+#pragma unroll
+    for (int it = 0; it < Q; ++it) A[it] = B[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+    SunSample s = load_sample(&sSample[0]);
+#define PAS_LOAD_T_SLOTS(S)                                                                          \
+    {                                                                                                \
+      const int y0_ = (S).y0 & 0xffff, y1_ = (S).y1, m_ = (S).y0 >> 16;                              \
+      if (m_ & 1) { const float4* p = T4 + (size_t)((y0_ & 1) == 0 ? y0_ : y1_) * WIDTH * Q + tid;   \
+        _Pragma("unroll") for (int it = 0; it < Q; ++it) A[it] = __ldg(p + it * WIDTH); }            \
+      if (m_ & 2) { const float4* p = T4 + (size_t)((y0_ & 1) == 1 ? y0_ : y1_) * WIDTH * Q + tid;   \
+        _Pragma("unroll") for (int it = 0; it < Q; ++it) B[it] = __ldg(p + it * WIDTH); }            \
+    }
+    if (WIDTH > 0) PAS_LOAD_T_SLOTS(s)
     for (int i = 0; i < kSamples; ++i) {
-      const SunSample s = load_sample(&sSample[i]);
+      if (WIDTH == 0) s = load_sample(&sSample[i]);
       float4* buf = sRow + (i & 1) * Q * pitch;
       // stage the transmittance row at r_i (lerp of the two bracketing rows), flat 16-byte vectors
-      {
+      if (WIDTH > 0) {
+        // weights of the even / odd slot: y0 carries 1 - wy, y1 carries wy (wy = 0 when y0 == y1)
+        const bool y0_odd = (s.y0 & 1) != 0;
+        const float w_a = y0_odd ? s.wy : 1.0f - s.wy, w_b = y0_odd ? 1.0f - s.wy : s.wy;
+#pragma unroll
+        for (int it = 0; it < Q; ++it) {
+          const float4 a = A[it], b = B[it];
+          buf[(tid % Q) * pitch + rot(tid / Q + it * (WIDTH / Q))] =
+              make_float4(fmaf(w_a, a.x, w_b * b.x), fmaf(w_a, a.y, w_b * b.y), fmaf(w_a, a.z, w_b * b.z),
+                          fmaf(w_a, a.w, w_b * b.w));
+        }
+      } else {
         const float4* pa = T4 + (size_t)s.y0 * t_w * Q;
         const float4* pb = T4 + (size_t)s.y1 * t_w * Q;
-        if (WIDTH > 0) {
-          float4 a[Q], b[Q];
-#pragma unroll
-          for (int it = 0; it < Q; ++it) {
-            a[it] = __ldg(pa + tid + it * WIDTH);
-            b[it] = __ldg(pb + tid + it * WIDTH);
-          }
-#pragma unroll
-          for (int it = 0; it < Q; ++it) {
-            buf[(tid % Q) * pitch + rot(tid / Q + it * (WIDTH / Q))] = lerp4(s.wy, a[it], b[it]);
-          }
-        } else {
-          for (int f = tid; f < t_w * Q; f += nthreads) {
-            buf[(f % Q) * pitch + rot(f / Q)] = lerp4(s.wy, __ldg(pa + f), __ldg(pb + f));
-          }
+        for (int f = tid; f < t_w * Q; f += nthreads) {
+          buf[(f % Q) * pitch + rot(f / Q)] = lerp4(s.wy, __ldg(pa + f), __ldg(pb + f));
         }
+      }
+      const SunSample cur = s;
+      if (WIDTH > 0 && i + 1 < kSamples) {
+        s = load_sample(&sSample[i + 1]);
+        PAS_LOAD_T_SLOTS(s)
       }
       __syncthreads();
       if (active) {
         // sun direction at the sample: r_i mu_s_i = r mu_s + d nu (functions.glsl:657)
-        const float r_i = f_rcp(s.inv_r);
-        const float p = f_clamp(fmaf(s.d, nu, r_mu_s), -r_i, r_i);
+        const float r_i = f_rcp(cur.inv_r);
+        const float p = f_clamp(fmaf(cur.d, nu, r_mu_s), -r_i, r_i);
         // GetTransmittanceToSun (functions.glsl:552-563): table x from the distance to the top
-        const float xt = f_clamp((f_dist_top(p, s.q) - s.d_min) * s.x_scale, 0.0f, x_max);
+        const float xt = f_clamp((f_dist_top(p, cur.q) - cur.d_min) * cur.x_scale, 0.0f, x_max);
         const Tap tu = make_tap_f(xt, t_w);
-        const float mu_s_i = p * s.inv_r;
-        const float sm = f_sat(fmaf(mu_s_i - s.cos_h, s.inv_sun_w, 0.5f));
+        const float mu_s_i = p * cur.inv_r;
+        const float sm = f_sat(fmaf(mu_s_i - cur.cos_h, cur.inv_sun_w, 0.5f));
         const float vis = sm * sm * fmaf(-2.0f, sm, 3.0f);
-        const float wr = vis * s.dens_r, wm = vis * s.dens_m;
+        const float wr = vis * cur.dens_r, wm = vis * cur.dens_m;
         const float4* t0 = buf + rot(tu.i0);
         const float4* t1 = buf + rot(tu.i1);
         const float4* tw4 = reinterpret_cast<const float4*>(sTw[i]);
@@ -658,6 +698,7 @@ single_scattering_kernel(const __grid_constant__ PasGeometry g,
         }
       }
     }
+#undef PAS_LOAD_T_SLOTS
   }
   if (!active) return;
   const size_t texel = ((size_t)k * mu_n + j) * width + x;
@@ -752,7 +793,7 @@ cudaError_t launch_single_nc(const PasGeometry& g, const PasSpectrum& s, const f
   const dim3 grid(g.sz.mu_n, k_end - k_begin);
   cudaError_t e;
   if (width == 256 && g.sz.t_w == 256) {
-    auto kern = single_scattering_kernel<NC, 256, 3, 256, true>;
+    auto kern = single_scattering_kernel<NC, 256, 2, 256, true>;  // 128 registers: the row slots stay in registers
     if ((e = prepare(kern, dyn)) != cudaSuccess) return e;
     kern<<<grid, 256, dyn, stream>>>(g, s, T, dR, dM, fin, k_begin);
   } else if (threads <= 256) {
