@@ -320,15 +320,28 @@ def run_b200(args, rank, world_size, local_rank):
                              "frac_fp32_peak": round(f / (ms * 1e-3) / 1e12 / peaks["fp32_tflops"], 4),
                              "frac_mufu_peak": round(u / (ms * 1e-3) / 1e9 / peaks["mufu_gops"], 4)}
     dom = max(kernels, key=lambda k: kernels[k]["ms"])
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    # ncu evidence of the same kernels (profiles/ncu_hot_kernels.json, made by tools/ncu_to_json.py
+    # from one `ncu --set full` capture on B200): DRAM bytes per launch = `traffic`, and the executed
+    # pipe utilisations, which is what bounds these kernels (the canonical flop count above credits
+    # the minimal formulation; the density kernel executes fewer instructions than that)
+    traffic, ncu = None, None
+    tpath = os.path.join(ROOT, "profiles", "ncu_hot_kernels.json")
     if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get(phase_key(dom))
+        ncu = json.load(open(tpath))
+        traffic = ncu["passes"].get(phase_key(dom), {}).get("traffic_bytes")
+        for name, k in kernels.items():
+            e = ncu["passes"].get(phase_key(name))
+            if e:
+                k["ncu"] = {m: e[m] for m in ("traffic_bytes", "fma_pipe_cycles_active_pct", "issue_active_pct",
+                                              "l1_data_pipe_wavefronts_pct", "dram_throughput_pct")}
     roofline = {
         "kernel": dom, "bound": "fp32", "achieved": kernels[dom]["tflops"], "peak": round(peaks["fp32_tflops"], 2),
         "unit": "TFLOP/s", "frac": kernels[dom]["frac_fp32_peak"], "traffic": traffic,
         "peak_source": "measured on this device by pas_measure_device_peaks (FMA microbenchmark); "
                        "MEASURED_PEAKS.json has no FP32 figure",
+        "achieved_is": "canonical FP32 flops of SURVEY.md 8(d) / live CUDA-event time of the pass; > peak "
+                       "means the kernel needs fewer flops than the canonical formulation counts",
+        "ncu_source": ncu["source"] if ncu else None,
         "mufu_peak_gops": round(peaks["mufu_gops"], 1),
         "whole_job": {"canonical_gflop": round(total_f / 1e9, 1), "canonical_mufu_gop": round(total_u / 1e9, 2),
                       "frac_fp32_peak": round(total_f / (ms_per_step * 1e-3) / 1e12 / (world_size * peaks["fp32_tflops"]), 4),
