@@ -18,6 +18,8 @@
 //
 // The azimuth samples come in pairs (phi, -phi) sharing cos(phi), hence nu2 and both phase
 // functions (functions.glsl:1246-1256): the loop runs over 16 cosines x 2 signs of sin(phi).
+#include <cooperative_groups.h>
+
 #include "pas_kernels.h"
 #include "pas_physics.cuh"
 
@@ -324,7 +326,8 @@ density_kernel_x2(const __grid_constant__ PasGeometry g, int NC, const PasDensit
                   const float* __restrict__ G, const float* __restrict__ cRk,
                   const float* __restrict__ cMk, const float* __restrict__ tabA,
                   const float* __restrict__ tabB, const float* __restrict__ dE,
-                  float* __restrict__ dJ, const __grid_constant__ PeerTables mirrors, int k_begin) {
+                  float* __restrict__ dJ, const __grid_constant__ PeerTables mirrors, int k_begin,
+                  int k_stride) {
   constexpr int NT = ORDER2 ? 2 : 1;
   constexpr int NP = CP / 2;
   extern __shared__ __align__(16) float smem_dyn[];
@@ -335,7 +338,7 @@ density_kernel_x2(const __grid_constant__ PasGeometry g, int NC, const PasDensit
 
   const int tid = threadIdx.x;
   const int i_mu_s = blockIdx.y;
-  const int k = k_begin + blockIdx.z;
+  const int k = k_begin + blockIdx.z * k_stride;
   const int mu_n = g.sz.mu_n, nu_n = g.sz.nu_n, mu_s_n = g.sz.mu_s_n, e_w = g.sz.e_w;
   const int width = nu_n * mu_s_n;
   const size_t layer = (size_t)k * mu_n * width;
@@ -420,9 +423,12 @@ density_kernel_x2(const __grid_constant__ PasGeometry g, int NC, const PasDensit
   __syncthreads();
 
   // ---- per-texel geometry (fp64, once) --------------------------------------------------------
+  constexpr int Q = CP / 4;
   const int texel = blockIdx.x * blockDim.x + tid;
-  if (texel >= mu_n * nu_n) return;
-  const int j = texel / nu_n, i_nu = texel % nu_n;
+  const bool active = texel < mu_n * nu_n;
+  // (the multi-GPU instantiation ends with cluster-wide barriers: its idle threads tag along on texel 0)
+  if (!active && !(MIRROR && Q > 1)) return;
+  const int j = active ? texel / nu_n : 0, i_nu = active ? texel % nu_n : 0;
   double mu_d, r_mu_d;
   bool hit_unused;
   scattering_row_mu(g, r, rho, j, &mu_d, &r_mu_d, &hit_unused);
@@ -501,13 +507,6 @@ density_kernel_x2(const __grid_constant__ PasGeometry g, int NC, const PasDensit
   }
 
   // ---- output: one interleaved texel (CP floats) per thread ---------------------------------------
-  // The texels of a block are 2 KB apart in the table (same column, consecutive (mu, nu)). Each warp
-  // transposes its 32 texels through shared memory so that Q = CP / 4 neighbouring lanes store the
-  // 16-byte vectors of ONE texel: a warp store then covers 32 / Q whole texels instead of 32 isolated
-  // 16-byte pieces. This matters for the copies sent to the other GPUs (multi-GPU: every rank needs
-  // this layer for its multiple-scattering rays): posted stores over NVLink travel as
-  // 64-byte instead of 16-byte packets. They are completed by the barrier kernel that follows.
-  constexpr int Q = CP / 4;
   if (!MIRROR || Q == 1) {
     const size_t offset = (layer + (size_t)j * width + i_nu * mu_s_n + i_mu_s) * CP;
 #pragma unroll
@@ -520,39 +519,51 @@ density_kernel_x2(const __grid_constant__ PasGeometry g, int NC, const PasDensit
     }
     return;
   }
-  const int lane = tid & 31, warp = tid >> 5;
-  // lanes of this warp that own a texel (the others returned before the direction loop)
-  const int n_live = min(32, mu_n * nu_n - (int)(blockIdx.x * blockDim.x + warp * 32));
-  const unsigned live = n_live >= 32 ? 0xffffffffu : ((1u << n_live) - 1u);
-  float4* stage = reinterpret_cast<float4*>(sDE + NP * e_pad) + warp * 32 * (Q + 1);  // [32][Q + 1]
+  // Multi-GPU: every rank needs this layer for its multiple-scattering rays, so the
+  // texels are also stored into the tables of the other GPUs: posted stores over NVLink, completed by
+  // the barrier kernel that follows the pass. The texels of one block are 2 KB apart (same mu_s
+  // column, consecutive (mu, nu)); stored thread by thread they would cross the link as isolated
+  // 16-byte packets. The CL blocks of a thread-block cluster own CL neighbouring columns, i.e.
+  // CL x 64 contiguous bytes per (mu, nu): each block parks its texels in shared memory, and after a
+  // cluster barrier each block writes 1 / CL of the (mu, nu) range for ALL the columns of the
+  // cluster, reading the other blocks' texels through distributed shared memory. CL * Q
+  // neighbouring lanes then store one contiguous run of CL * 64 bytes (256 B at CL = 4).
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int CL = (int)cluster.dim_blocks().y;
+  const int crank = (int)cluster.block_rank();       // cluster dims are (1, CL, 1)
+  float4* stage = reinterpret_cast<float4*>(sDE + NP * e_pad);  // [256][Q + 1]
 #pragma unroll
   for (int q = 0; q < Q; ++q) {
-    stage[lane * (Q + 1) + q] = make_float4(acc[2 * q].x, acc[2 * q].y, acc[2 * q + 1].x, acc[2 * q + 1].y);
+    stage[tid * (Q + 1) + q] = make_float4(acc[2 * q].x, acc[2 * q].y, acc[2 * q + 1].x, acc[2 * q + 1].y);
   }
-  __syncwarp(live);
-#pragma unroll
-  for (int it = 0; it < Q; ++it) {
-    const int idx = it * 32 + lane;
-    const int t = idx / Q, q = idx % Q;      // texel of lane t of this warp, vector q
-    if (!((live >> t) & 1u)) continue;
-    const int tex = blockIdx.x * blockDim.x + warp * 32 + t;
-    const size_t offset = (layer + (size_t)(tex / nu_n) * width + (tex % nu_n) * mu_s_n + i_mu_s) * CP + 4 * q;
-    const float4 v = stage[t * (Q + 1) + q];
+  cluster.sync();
+  const int per = (int)blockDim.x / CL;              // (mu, nu) texels written by this block
+  const int col0 = i_mu_s - crank;                   // first column of the cluster
+  for (int idx = tid; idx < per * CL * Q; idx += blockDim.x) {
+    const int q = idx % Q, c = (idx / Q) % CL, t = crank * per + idx / (Q * CL);
+    const int tex = blockIdx.x * blockDim.x + t;
+    if (tex >= mu_n * nu_n) continue;
+    const float4* src = cluster.map_shared_rank(stage, c);
+    const float4 v = src[t * (Q + 1) + q];
+    const size_t offset = (layer + (size_t)(tex / nu_n) * width + (tex % nu_n) * mu_s_n + col0 + c) * CP + 4 * q;
     *reinterpret_cast<float4*>(dJ + offset) = v;
     for (int p = 0; p < mirrors.n; ++p) *reinterpret_cast<float4*>(mirrors.tab[p] + offset) = v;
   }
+  cluster.sync();  // the shared memory of a block must outlive the reads of its cluster mates
 }
 
 template <int CP, bool ORDER2, int NUM, bool MIRROR>
 cudaError_t launch_one(const PasGeometry& g, int nc, const PasDensityDir* dirs, const float* G,
                        const float* cR, const float* cM, const float* tabA, const float* tabB,
-                       const float* dE, float* dJ, const PeerTables& mirrors, int k_begin, int k_end,
+                       const float* dE, float* dJ, const PeerTables& mirrors, LayerSet layers,
                        cudaStream_t stream) {
   const int threads = 256;
   const int texels = g.sz.mu_n * g.sz.nu_n;
-  dim3 grid((texels + threads - 1) / threads, g.sz.mu_s_n, k_end - k_begin);
+  if (layers.count() == 0) return cudaSuccess;
+  dim3 grid((texels + threads - 1) / threads, g.sz.mu_s_n, layers.count());
   constexpr int Q = CP / 4;
-  // irradiance row + differences, then (MIRROR) the per-warp output staging [8 warps][32][Q + 1] float4
+  // irradiance row + differences, then (MIRROR) the output staging [256][Q + 1] float4
   const size_t dyn = (size_t)2 * CP * (g.sz.e_w + kNG + 1) * sizeof(float) +
                      (MIRROR && Q > 1 ? (size_t)(threads / 32) * 32 * (Q + 1) * sizeof(float4) : 0);
   auto kern = density_kernel_x2<CP, ORDER2, NUM, MIRROR>;
@@ -560,7 +571,29 @@ cudaError_t launch_one(const PasGeometry& g, int nc, const PasDensityDir* dirs, 
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
     if (e != cudaSuccess) return e;
   }
-  kern<<<grid, threads, dyn, stream>>>(g, nc, dirs, G, cR, cM, tabA, tabB, dE, dJ, mirrors, k_begin);
+  if (MIRROR && Q > 1) {
+    // clusters of 2 (or 1) neighbouring mu_s columns: see the output stage of the kernel
+    // measured on 8 / 4 / 2 B200 (15 channels): pairs of columns (128-byte runs) beat single columns
+    // from 3 mirrors on (1.54 vs 1.69 ms, 2.31 vs 2.35 ms); clusters of 4 lose to the longer wait at
+    // the cluster barrier (1.59 ms); with one mirror the plain layout wins (3.96 vs 4.08 ms)
+    const unsigned cl = (mirrors.n >= 3 && g.sz.mu_s_n % 2 == 0) ? 2 : 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(threads);
+    cfg.dynamicSmemBytes = dyn;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 1;
+    attr[0].val.clusterDim.y = cl;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, g, nc, dirs, G, cR, cM, tabA, tabB, dE, dJ, mirrors, layers.begin,
+                              layers.stride);
+  }
+  kern<<<grid, threads, dyn, stream>>>(g, nc, dirs, G, cR, cM, tabA, tabB, dE, dJ, mirrors, layers.begin,
+                              layers.stride);
   return cudaGetLastError();
 }
 
@@ -568,14 +601,14 @@ template <int CP, bool MIRROR>
 cudaError_t launch_cp(const PasGeometry& g, int nc, const PasDensityDir* dirs, const float* G,
                       const float* cR, const float* cM, const float* dR, const float* dM,
                       const float* dS, const float* dE, int order, float* dJ,
-                      const PeerTables& mirrors, int k_begin, int k_end, cudaStream_t stream) {
+                      const PeerTables& mirrors, LayerSet layers, cudaStream_t stream) {
   const bool wide = g.sz.nu_n > 8;
   if (order == 2) {
-    return wide ? launch_one<CP, true, 16, MIRROR>(g, nc, dirs, G, cR, cM, dR, dM, dE, dJ, mirrors, k_begin, k_end, stream)
-                : launch_one<CP, true, 8, MIRROR>(g, nc, dirs, G, cR, cM, dR, dM, dE, dJ, mirrors, k_begin, k_end, stream);
+    return wide ? launch_one<CP, true, 16, MIRROR>(g, nc, dirs, G, cR, cM, dR, dM, dE, dJ, mirrors, layers, stream)
+                : launch_one<CP, true, 8, MIRROR>(g, nc, dirs, G, cR, cM, dR, dM, dE, dJ, mirrors, layers, stream);
   }
-  return wide ? launch_one<CP, false, 16, MIRROR>(g, nc, dirs, G, cR, cM, dS, nullptr, dE, dJ, mirrors, k_begin, k_end, stream)
-              : launch_one<CP, false, 8, MIRROR>(g, nc, dirs, G, cR, cM, dS, nullptr, dE, dJ, mirrors, k_begin, k_end, stream);
+  return wide ? launch_one<CP, false, 16, MIRROR>(g, nc, dirs, G, cR, cM, dS, nullptr, dE, dJ, mirrors, layers, stream)
+              : launch_one<CP, false, 8, MIRROR>(g, nc, dirs, G, cR, cM, dS, nullptr, dE, dJ, mirrors, layers, stream);
 }
 
 }  // namespace
@@ -584,7 +617,7 @@ cudaError_t launch_scattering_density(const PasGeometry& g, const PasSpectrum& s
                                       const PasDensityDir* dirs, const float* G, const float* cR,
                                       const float* cM, const float* dR, const float* dM,
                                       const float* dS, const float* dE, int order, float* dJ,
-                                      const PeerTables& mirrors, int k_begin, int k_end,
+                                      const PeerTables& mirrors, LayerSet layers,
                                       cudaStream_t stream) {
   if (g.sz.nu_n < 2 || g.sz.nu_n > PAS_MAX_NU) return cudaErrorInvalidValue;
   if (!channel_count_supported(s.nc)) return cudaErrorInvalidValue;
@@ -592,10 +625,8 @@ cudaError_t launch_scattering_density(const PasGeometry& g, const PasSpectrum& s
   switch (PAS_CHANNEL_PITCH(s.nc)) {
 #define PAS_CASE(CP)                                                                                   \
   case CP:                                                                                             \
-    return mirror ? launch_cp<CP, true>(g, s.nc, dirs, G, cR, cM, dR, dM, dS, dE, order, dJ, mirrors,  \
-                                        k_begin, k_end, stream)                                        \
-                  : launch_cp<CP, false>(g, s.nc, dirs, G, cR, cM, dR, dM, dS, dE, order, dJ, mirrors, \
-                                         k_begin, k_end, stream);
+    return mirror ? launch_cp<CP, true>(g, s.nc, dirs, G, cR, cM, dR, dM, dS, dE, order, dJ, mirrors, layers, stream)                                        \
+                  : launch_cp<CP, false>(g, s.nc, dirs, G, cR, cM, dR, dM, dS, dE, order, dJ, mirrors, layers, stream);
     PAS_CASE(4) PAS_CASE(8) PAS_CASE(16)
 #undef PAS_CASE
     default: return cudaErrorInvalidValue;

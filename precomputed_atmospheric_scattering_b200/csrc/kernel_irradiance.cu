@@ -20,7 +20,7 @@ __global__ void __launch_bounds__(kThreads)
 indirect_irradiance_kernel(const __grid_constant__ PasGeometry g,
                            const __grid_constant__ PasSpectrum sp, const float* __restrict__ tabA,
                            const float* __restrict__ tabB, float* __restrict__ dE, FinalTables fin,
-                           int j_begin, int k_begin, int k_end) {
+                           int j_begin, int k_begin, int k_end, int k_stride) {
   constexpr int NT = ORDER1 ? 2 : 1;
   constexpr int CP = PAS_CHANNEL_PITCH(NC);
   __shared__ float sV[NT][PAS_IRR_THETA][NC][PAS_MAX_NU];
@@ -55,7 +55,7 @@ indirect_irradiance_kernel(const __grid_constant__ PasGeometry g,
       const float w = ((corner & 4) ? tk.w : 1.f - tk.w) * ((corner & 2) ? tj.w : 1.f - tj.w) *
                       ((corner & 1) ? ts.w : 1.f - ts.w);
       // r-slab sharding: layers owned by other ranks contribute through their partial sums
-      if (kk < k_begin || kk >= k_end) continue;
+      if (kk < k_begin || kk >= k_end || (kk - k_begin) % k_stride != 0) continue;
       v = fmaf(w, p[(kk * layer_stride + (size_t)jj * width + s * mu_s_n + ii) * CP], v);
     }
     sV[t][l][c][s] = v;
@@ -129,14 +129,14 @@ indirect_irradiance_kernel(const __grid_constant__ PasGeometry g,
 template <int NC>
 cudaError_t launch_nc(const PasGeometry& g, const PasSpectrum& s, const float* dR, const float* dM,
                       const float* dS, int order, float* dE, FinalTables fin, int j_begin,
-                      int j_end, int k_begin, int k_end, cudaStream_t stream) {
+                      int j_end, LayerSet layers, cudaStream_t stream) {
   dim3 grid(g.sz.e_w, j_end - j_begin);
   if (order == 1) {
     indirect_irradiance_kernel<NC, true><<<grid, kThreads, 0, stream>>>(g, s, dR, dM, dE, fin, j_begin,
-                                                                        k_begin, k_end);
+                                                                        layers.begin, layers.end, layers.stride);
   } else {
     indirect_irradiance_kernel<NC, false><<<grid, kThreads, 0, stream>>>(g, s, dS, nullptr, dE, fin,
-                                                                         j_begin, k_begin, k_end);
+                                                                         j_begin, layers.begin, layers.end, layers.stride);
   }
   return cudaGetLastError();
 }
@@ -145,12 +145,12 @@ cudaError_t launch_nc(const PasGeometry& g, const PasSpectrum& s, const float* d
 
 cudaError_t launch_indirect_irradiance(const PasGeometry& g, const PasSpectrum& s, const float* dR,
                                        const float* dM, const float* dS, int order, float* dE,
-                                       FinalTables fin, int j_begin, int j_end, int k_begin,
-                                       int k_end, cudaStream_t stream) {
+                                       FinalTables fin, int j_begin, int j_end, LayerSet layers,
+                                       cudaStream_t stream) {
   if (g.sz.nu_n > PAS_MAX_NU) return cudaErrorInvalidValue;
   switch (s.nc) {
 #define PAS_CASE(N) \
-  case N: return launch_nc<N>(g, s, dR, dM, dS, order, dE, fin, j_begin, j_end, k_begin, k_end, stream);
+  case N: return launch_nc<N>(g, s, dR, dM, dS, order, dE, fin, j_begin, j_end, layers, stream);
     PAS_CASE(3) PAS_CASE(4) PAS_CASE(8) PAS_CASE(15) PAS_CASE(16)
 #undef PAS_CASE
     default: return cudaErrorInvalidValue;

@@ -214,14 +214,14 @@ __global__ void __launch_bounds__(MAXT, MINB)
 multiple_scattering_kernel(const __grid_constant__ PasGeometry g,
                            const __grid_constant__ PasSpectrum sp, const float* __restrict__ T,
                            const float* __restrict__ dJ, float* __restrict__ dS, FinalTables fin,
-                           int k_begin) {
+                           int k_begin, int k_stride) {
   constexpr int CP = PAS_CHANNEL_PITCH(NC), Q = CP / 4;
   extern __shared__ __align__(16) float smem_dyn[];
   __shared__ ScatterSample sSample[kSamples];
   __shared__ __align__(16) float sTw[kSamples][CP];
 
   const int tid = threadIdx.x;
-  const int j = blockIdx.x, k = k_begin + blockIdx.y;
+  const int j = blockIdx.x, k = k_begin + blockIdx.y * k_stride;
   const int mu_n = g.sz.mu_n, nu_n = g.sz.nu_n, mu_s_n = g.sz.mu_s_n;
   const int width = WIDTH > 0 ? WIDTH : nu_n * mu_s_n;
   const int nthreads = WIDTH > 0 ? WIDTH : (int)blockDim.x;
@@ -363,7 +363,7 @@ __global__ void __launch_bounds__(256, 2)
 multiple_scattering_rows_kernel(const __grid_constant__ PasGeometry g,
                                 const __grid_constant__ PasSpectrum sp, const float* __restrict__ T,
                                 const float* __restrict__ dJ, float* __restrict__ dS,
-                                FinalTables fin, int k_begin) {
+                                FinalTables fin, int k_begin, int k_stride) {
   constexpr int CP = PAS_CHANNEL_PITCH(NC), Q = CP / 4, WIDTH = 256;
   static_assert(sizeof(SlotSample) == sizeof(ScatterSample), "plan is rewritten in place");
   extern __shared__ __align__(16) float smem_dyn[];
@@ -373,7 +373,7 @@ multiple_scattering_rows_kernel(const __grid_constant__ PasGeometry g,
   __shared__ int sCount[WIDTH / 32];
 
   const int tid = threadIdx.x;
-  const int j = blockIdx.x, k = k_begin + blockIdx.y;
+  const int j = blockIdx.x, k = k_begin + blockIdx.y * k_stride;
   const int mu_n = g.sz.mu_n, nu_n = g.sz.nu_n, mu_s_n = g.sz.mu_s_n;
   constexpr int pitch = ((WIDTH + 7) & ~7) + 8 / Q;
   float4* sRow = reinterpret_cast<float4*>(smem_dyn);  // [2][Q * pitch]
@@ -573,14 +573,14 @@ __global__ void __launch_bounds__(MAXT, MINB)
 single_scattering_kernel(const __grid_constant__ PasGeometry g,
                          const __grid_constant__ PasSpectrum sp, const float* __restrict__ T,
                          float* __restrict__ dR, float* __restrict__ dM, FinalTables fin,
-                         int k_begin) {
+                         int k_begin, int k_stride) {
   constexpr int CP = PAS_CHANNEL_PITCH(NC), Q = CP / 4;
   extern __shared__ __align__(16) float smem_dyn[];
   __shared__ SunSample sSample[kSamples];
   __shared__ __align__(16) float sTw[kSamples][CP];
 
   const int tid = threadIdx.x;
-  const int j = blockIdx.x, k = k_begin + blockIdx.y;
+  const int j = blockIdx.x, k = k_begin + blockIdx.y * k_stride;
   const int mu_n = g.sz.mu_n, nu_n = g.sz.nu_n, mu_s_n = g.sz.mu_s_n;
   const int t_w = WIDTH > 0 ? WIDTH : g.sz.t_w;
   const int width = WIDTH > 0 ? WIDTH : nu_n * mu_s_n;
@@ -752,58 +752,60 @@ cudaError_t prepare(Kern kern, size_t dyn) {
 
 template <int NC>
 cudaError_t launch_multiple_nc(const PasGeometry& g, const PasSpectrum& s, const float* T,
-                               const float* dJ, float* dS, FinalTables fin, int k_begin, int k_end,
+                               const float* dJ, float* dS, FinalTables fin, LayerSet layers,
                                cudaStream_t stream) {
   constexpr int CP = PAS_CHANNEL_PITCH(NC), Q = CP / 4;
   const int width = g.sz.nu_n * g.sz.mu_s_n;
   if (width > 1024) return cudaErrorInvalidValue;
   const int threads = round_up32(width < kSamples ? kSamples : width);
   const size_t dyn = (size_t)2 * Q * (((width + 7) & ~7) + 8 / Q) * sizeof(float4);
-  const dim3 grid(g.sz.mu_n, k_end - k_begin);
+  if (layers.count() == 0) return cudaSuccess;
+  const dim3 grid(g.sz.mu_n, layers.count());
   cudaError_t e;
   if (width == 256 && Q > 1) {
     auto kern = multiple_scattering_rows_kernel<NC>;  // the reference's 8 x 32 row
     if ((e = prepare(kern, dyn)) != cudaSuccess) return e;
-    kern<<<grid, 256, dyn, stream>>>(g, s, T, dJ, dS, fin, k_begin);
+    kern<<<grid, 256, dyn, stream>>>(g, s, T, dJ, dS, fin, layers.begin, layers.stride);
   } else if (width == 256) {
     auto kern = multiple_scattering_kernel<NC, 256, 3, 256>;
     if ((e = prepare(kern, dyn)) != cudaSuccess) return e;
-    kern<<<grid, 256, dyn, stream>>>(g, s, T, dJ, dS, fin, k_begin);
+    kern<<<grid, 256, dyn, stream>>>(g, s, T, dJ, dS, fin, layers.begin, layers.stride);
   } else if (threads <= 256) {
     auto kern = multiple_scattering_kernel<NC, 256, 3, 0>;
     if ((e = prepare(kern, dyn)) != cudaSuccess) return e;
-    kern<<<grid, threads, dyn, stream>>>(g, s, T, dJ, dS, fin, k_begin);
+    kern<<<grid, threads, dyn, stream>>>(g, s, T, dJ, dS, fin, layers.begin, layers.stride);
   } else {
     auto kern = multiple_scattering_kernel<NC, 1024, 1, 0>;
     if ((e = prepare(kern, dyn)) != cudaSuccess) return e;
-    kern<<<grid, threads, dyn, stream>>>(g, s, T, dJ, dS, fin, k_begin);
+    kern<<<grid, threads, dyn, stream>>>(g, s, T, dJ, dS, fin, layers.begin, layers.stride);
   }
   return cudaGetLastError();
 }
 
 template <int NC>
 cudaError_t launch_single_nc(const PasGeometry& g, const PasSpectrum& s, const float* T, float* dR,
-                             float* dM, FinalTables fin, int k_begin, int k_end,
+                             float* dM, FinalTables fin, LayerSet layers,
                              cudaStream_t stream) {
   constexpr int CP = PAS_CHANNEL_PITCH(NC), Q = CP / 4;
   const int width = g.sz.nu_n * g.sz.mu_s_n;
   if (width > 1024) return cudaErrorInvalidValue;
   const int threads = round_up32(width < kSamples ? kSamples : width);
   const size_t dyn = (size_t)2 * Q * (((g.sz.t_w + 7) & ~7) + 8 / Q) * sizeof(float4);
-  const dim3 grid(g.sz.mu_n, k_end - k_begin);
+  if (layers.count() == 0) return cudaSuccess;
+  const dim3 grid(g.sz.mu_n, layers.count());
   cudaError_t e;
   if (width == 256 && g.sz.t_w == 256) {
     auto kern = single_scattering_kernel<NC, 256, 2, 256, true>;  // 128 registers: the row slots stay in registers
     if ((e = prepare(kern, dyn)) != cudaSuccess) return e;
-    kern<<<grid, 256, dyn, stream>>>(g, s, T, dR, dM, fin, k_begin);
+    kern<<<grid, 256, dyn, stream>>>(g, s, T, dR, dM, fin, layers.begin, layers.stride);
   } else if (threads <= 256) {
     auto kern = single_scattering_kernel<NC, 256, 3, 0, false>;
     if ((e = prepare(kern, dyn)) != cudaSuccess) return e;
-    kern<<<grid, threads, dyn, stream>>>(g, s, T, dR, dM, fin, k_begin);
+    kern<<<grid, threads, dyn, stream>>>(g, s, T, dR, dM, fin, layers.begin, layers.stride);
   } else {
     auto kern = single_scattering_kernel<NC, 1024, 1, 0, false>;
     if ((e = prepare(kern, dyn)) != cudaSuccess) return e;
-    kern<<<grid, threads, dyn, stream>>>(g, s, T, dR, dM, fin, k_begin);
+    kern<<<grid, threads, dyn, stream>>>(g, s, T, dR, dM, fin, layers.begin, layers.stride);
   }
   return cudaGetLastError();
 }
@@ -811,11 +813,11 @@ cudaError_t launch_single_nc(const PasGeometry& g, const PasSpectrum& s, const f
 }  // namespace
 
 cudaError_t launch_multiple_scattering(const PasGeometry& g, const PasSpectrum& s, const float* T,
-                                       const float* dJ, float* dS, FinalTables fin, int k_begin,
-                                       int k_end, cudaStream_t stream) {
+                                       const float* dJ, float* dS, FinalTables fin, LayerSet layers,
+                                       cudaStream_t stream) {
   switch (s.nc) {
 #define PAS_CASE(N) \
-  case N: return launch_multiple_nc<N>(g, s, T, dJ, dS, fin, k_begin, k_end, stream);
+  case N: return launch_multiple_nc<N>(g, s, T, dJ, dS, fin, layers, stream);
     PAS_CASE(3) PAS_CASE(4) PAS_CASE(8) PAS_CASE(15) PAS_CASE(16)
 #undef PAS_CASE
     default: return cudaErrorInvalidValue;
@@ -823,11 +825,11 @@ cudaError_t launch_multiple_scattering(const PasGeometry& g, const PasSpectrum& 
 }
 
 cudaError_t launch_single_scattering(const PasGeometry& g, const PasSpectrum& s, const float* T,
-                                     float* dR, float* dM, FinalTables fin, int k_begin, int k_end,
+                                     float* dR, float* dM, FinalTables fin, LayerSet layers,
                                      cudaStream_t stream) {
   switch (s.nc) {
 #define PAS_CASE(N) \
-  case N: return launch_single_nc<N>(g, s, T, dR, dM, fin, k_begin, k_end, stream);
+  case N: return launch_single_nc<N>(g, s, T, dR, dM, fin, layers, stream);
     PAS_CASE(3) PAS_CASE(4) PAS_CASE(8) PAS_CASE(15) PAS_CASE(16)
 #undef PAS_CASE
     default: return cudaErrorInvalidValue;

@@ -32,6 +32,14 @@ struct PeerTables {
   float* tab[PAS_MAX_PEERS];
 };
 
+// The scattering layers a launch works on: begin, begin + stride, ... < end. One GPU: all of them.
+// Several GPUs: a contiguous slab per rank (NCCL exchange) or every world-th layer (peer exchange:
+// the cost of a layer grows with its altitude, interleaving balances the ranks).
+struct LayerSet {
+  int begin, end, stride;
+  int count() const { return end > begin ? (end - begin + stride - 1) / stride : 0; }
+};
+
 // T[c][j][i] = transmittance to the top boundary (ComputeTransmittanceToTopAtmosphereBoundaryTexture,
 // functions.glsl:454-463). One warp per texel, 501 samples split across lanes, fp64.
 cudaError_t launch_transmittance(const PasGeometry& g, const PasSpectrum& s, float* T,
@@ -64,7 +72,7 @@ cudaError_t launch_density_setup(const PasGeometry& g, const PasSpectrum& s, con
 // Single scattering (functions.glsl:933-945) for layers [k_begin, k_end) + fused epilogue
 // S.rgb (+)= L.dR, S.a (+)= (L.dM).r, M (+)= L.dM (model.cc:142-157).
 cudaError_t launch_single_scattering(const PasGeometry& g, const PasSpectrum& s, const float* T,
-                                     float* dR, float* dM, FinalTables fin, int k_begin, int k_end,
+                                     float* dR, float* dM, FinalTables fin, LayerSet layers,
                                      cudaStream_t stream);
 
 // Scattering density of `order` >= 2 (functions.glsl:1348-1367) for layers [k_begin, k_end).
@@ -74,7 +82,7 @@ cudaError_t launch_scattering_density(const PasGeometry& g, const PasSpectrum& s
                                       const PasDensityDir* dirs, const float* G, const float* cR,
                                       const float* cM, const float* dR, const float* dM,
                                       const float* dS, const float* dE, int order, float* dJ,
-                                      const PeerTables& mirrors, int k_begin, int k_end,
+                                      const PeerTables& mirrors, LayerSet layers,
                                       cudaStream_t stream);
 
 // Indirect irradiance from radiance of `order` (1: dR/dM with phase functions, else dS)
@@ -83,14 +91,14 @@ cudaError_t launch_scattering_density(const PasGeometry& g, const PasSpectrum& s
 // owned by this rank; the partial sums are all-reduced by the caller).
 cudaError_t launch_indirect_irradiance(const PasGeometry& g, const PasSpectrum& s, const float* dR,
                                        const float* dM, const float* dS, int order, float* dE,
-                                       FinalTables fin, int j_begin, int j_end, int k_begin,
-                                       int k_end, cudaStream_t stream);
+                                       FinalTables fin, int j_begin, int j_end, LayerSet layers,
+                                       cudaStream_t stream);
 
 // Multiple scattering (functions.glsl:1369-1383) for layers [k_begin, k_end) + fused
 // S.rgb += L.dS / RayleighPhaseFunction(nu) (model.cc:192-208).
 cudaError_t launch_multiple_scattering(const PasGeometry& g, const PasSpectrum& s, const float* T,
-                                       const float* dJ, float* dS, FinalTables fin, int k_begin,
-                                       int k_end, cudaStream_t stream);
+                                       const float* dJ, float* dS, FinalTables fin, LayerSet layers,
+                                       cudaStream_t stream);
 
 // ---- multi-GPU exchange over peer memory (peer_exchange.cu) ---------------------------------------
 struct PeerFlags {                 // flags[r]: the flag array of rank r (own memory or IPC mapping)
@@ -104,9 +112,10 @@ struct PeerTargets {               // destinations of a push: the same buffer on
 };
 // Cross-GPU barrier number `epoch` (epochs increase by one per barrier, in step on every rank).
 cudaError_t launch_peer_barrier(const PeerFlags& f, unsigned epoch, cudaStream_t stream);
-// Copies src[offset, offset + bytes) to the same byte range of every target.
+// Copies `chunks` byte ranges [offset + i * stride, offset + i * stride + bytes) of src to the same
+// ranges of every target.
 cudaError_t launch_peer_push(const void* src, size_t bytes, size_t offset_bytes, const PeerTargets& t,
-                             cudaStream_t stream);
+                             cudaStream_t stream, int chunks = 1, size_t stride_bytes = 0);
 // out[i] = sum over ranks r (in rank order) of parts[r * stride + i].
 cudaError_t launch_sum_partials(const float* parts, int world, size_t stride, int n, float* out,
                                 cudaStream_t stream);

@@ -43,11 +43,15 @@ __global__ void peer_barrier_kernel(PeerFlags f, unsigned epoch, unsigned long l
   __threadfence_system();
 }
 
+// `chunks` ranges of n elements each, the first at `offset`, `stride` elements apart.
 template <typename V>
-__global__ void peer_push_kernel(const V* __restrict__ src, size_t n, size_t offset, PeerTargets t) {
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    const V v = src[offset + i];
-    for (int p = 0; p < t.n; ++p) reinterpret_cast<V*>(t.dst[p])[offset + i] = v;
+__global__ void peer_push_kernel(const V* __restrict__ src, size_t n, size_t offset, size_t stride,
+                                 int chunks, PeerTargets t) {
+  const size_t total = n * (size_t)chunks;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t at = offset + (i / n) * stride + i % n;
+    const V v = src[at];
+    for (int p = 0; p < t.n; ++p) reinterpret_cast<V*>(t.dst[p])[at] = v;
   }
 }
 
@@ -68,17 +72,19 @@ cudaError_t launch_peer_barrier(const PeerFlags& f, unsigned epoch, cudaStream_t
 }
 
 cudaError_t launch_peer_push(const void* src, size_t bytes, size_t offset_bytes, const PeerTargets& t,
-                             cudaStream_t stream) {
-  if (bytes == 0 || t.n == 0) return cudaSuccess;
-  if (bytes % 16 == 0 && offset_bytes % 16 == 0) {
-    const size_t n = bytes / 16;
-    const int blocks = (int)((n + 255) / 256 < 592 ? (n + 255) / 256 : 592);
-    peer_push_kernel<uint4><<<blocks, 256, 0, stream>>>(static_cast<const uint4*>(src), n, offset_bytes / 16, t);
+                             cudaStream_t stream, int chunks, size_t stride_bytes) {
+  if (bytes == 0 || t.n == 0 || chunks <= 0) return cudaSuccess;
+  if (bytes % 16 == 0 && offset_bytes % 16 == 0 && stride_bytes % 16 == 0) {
+    const size_t n = bytes / 16, total = n * chunks;
+    const int blocks = (int)((total + 255) / 256 < 592 ? (total + 255) / 256 : 592);
+    peer_push_kernel<uint4><<<blocks, 256, 0, stream>>>(static_cast<const uint4*>(src), n, offset_bytes / 16,
+                                                        stride_bytes / 16, chunks, t);
   } else {
-    if (bytes % 4 != 0 || offset_bytes % 4 != 0) return cudaErrorInvalidValue;
-    const size_t n = bytes / 4;
-    const int blocks = (int)((n + 255) / 256 < 592 ? (n + 255) / 256 : 592);
-    peer_push_kernel<float><<<blocks, 256, 0, stream>>>(static_cast<const float*>(src), n, offset_bytes / 4, t);
+    if (bytes % 4 != 0 || offset_bytes % 4 != 0 || stride_bytes % 4 != 0) return cudaErrorInvalidValue;
+    const size_t n = bytes / 4, total = n * chunks;
+    const int blocks = (int)((total + 255) / 256 < 592 ? (total + 255) / 256 : 592);
+    peer_push_kernel<float><<<blocks, 256, 0, stream>>>(static_cast<const float*>(src), n, offset_bytes / 4,
+                                                        stride_bytes / 4, chunks, t);
   }
   return cudaGetLastError();
 }
