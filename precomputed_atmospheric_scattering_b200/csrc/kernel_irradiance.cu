@@ -39,12 +39,25 @@ indirect_irradiance_kernel(const __grid_constant__ PasGeometry g,
   const Tap tk = make_tap(rho / g.H * (r_n - 1), r_n);
   const Tap ts = make_tap(scattering_x_from_mu_s(g, mu_s), mu_s_n);
 
+  // per-ring and per-azimuth constants, once per block (fp64 trigonometry, then fp32)
+  __shared__ Tap sTj[PAS_IRR_THETA];
+  __shared__ float sSinT[PAS_IRR_THETA], sCosT[PAS_IRR_THETA], sCosP[PAS_IRR_PHI / 2];
+  if (tid < PAS_IRR_THETA) {
+    const double theta = (tid + 0.5) * (kPi / (2 * PAS_IRR_THETA));
+    sTj[tid] = make_tap(scattering_y_from_mu(g, r, rho, cos(theta), false), mu_n);
+    sSinT[tid] = (float)sin(theta);
+    sCosT[tid] = (float)cos(theta);
+  } else if (tid >= 32 && tid < 32 + PAS_IRR_PHI / 2) {
+    const double phi = (tid - 32 + 0.5) * (kPi / (PAS_IRR_PHI / 2));
+    sCosP[tid - 32] = (float)cos(phi);
+  }
+  __syncthreads();
+
   // stage: reduce (r, mu, mu_s) once per (ring, channel, slab)
   for (int idx = tid; idx < NT * PAS_IRR_THETA * NC * nu_n; idx += kThreads) {
     const int c = idx % NC, s = (idx / NC) % nu_n, l = (idx / (nu_n * NC)) % PAS_IRR_THETA;
     const int t = idx / (nu_n * NC * PAS_IRR_THETA);
-    const double theta = (l + 0.5) * (kPi / (2 * PAS_IRR_THETA));
-    const Tap tj = make_tap(scattering_y_from_mu(g, r, rho, cos(theta), false), mu_n);
+    const Tap tj = sTj[l];
     const float* p = (t == 0 ? tabA : tabB) + c;  // interleaved: tab[texel * CP + c]
     float v = 0.f;
 #pragma unroll
@@ -73,9 +86,7 @@ indirect_irradiance_kernel(const __grid_constant__ PasGeometry g,
   for (int c = 0; c < NC; ++c) acc[c] = 0.f;
   for (int d = tid; d < PAS_IRR_THETA * (PAS_IRR_PHI / 2); d += kThreads) {
     const int l = d / (PAS_IRR_PHI / 2), m = d % (PAS_IRR_PHI / 2);
-    const double theta = (l + 0.5) * (kPi / (2 * PAS_IRR_THETA));
-    const double phi = (m + 0.5) * (kPi / (PAS_IRR_PHI / 2));
-    const float st = (float)sin(theta), ct = (float)cos(theta), cp = (float)cos(phi);
+    const float st = sSinT[l], ct = sCosT[l], cp = sCosP[m];
     // domega * omega.z, both azimuth signs (functions.glsl:1500-1507)
     const float w = 2.0f * ct * st * (float)((kPi / (2 * PAS_IRR_THETA)) * (kPi / (PAS_IRR_PHI / 2)));
     const float nu = fmaf(cp * st, sx, ct * sz);

@@ -19,7 +19,7 @@ __device__ __forceinline__ double warp_sum(double v) {
 __global__ void __launch_bounds__(256)
 transmittance_kernel(const __grid_constant__ PasGeometry g, const __grid_constant__ PasSpectrum s,
                      float* __restrict__ T, const __grid_constant__ PeerTables mirrors, int j_begin,
-                     int j_end) {
+                     int j_end, const __grid_constant__ RgbExtinction rgb, float* __restrict__ rgba) {
   const int texel = j_begin * g.sz.t_w + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
   const int lane = threadIdx.x & 31;
   if (texel >= j_end * g.sz.t_w) return;
@@ -56,6 +56,16 @@ transmittance_kernel(const __grid_constant__ PasGeometry g, const __grid_constan
     T[(size_t)texel * cp + lane] = t;
     // multi-GPU: every rank computes a band of rows and stores it to all the others
     for (int p = 0; p < mirrors.n; ++p) mirrors.tab[p][(size_t)texel * cp + lane] = t;
+  }
+  // The optical lengths do not depend on the wavelength: the final RGBA transmittance texture at
+  // 680 / 550 / 440 nm (model.cc:951-963) costs three more exponentials, on the idle lanes 16..19.
+  if (rgba != nullptr && lane >= 16 && lane < 20) {
+    const int c = lane - 16;
+    float t = 1.0f;  // alpha
+    if (c < 3) {
+      t = (float)exp(-(rgb.beta_r[c] * acc[0] + rgb.beta_m_ext[c] * acc[1] + rgb.beta_abs[c] * acc[2]));
+    }
+    rgba[(size_t)texel * 4 + c] = t;
   }
 }
 
@@ -190,8 +200,22 @@ cudaError_t launch_planar_to_interleaved(const float* src, size_t n_texels, int 
 }
 
 cudaError_t launch_transmittance(const PasGeometry& g, const PasSpectrum& s, float* T,
-                                 cudaStream_t stream) {
-  return launch_transmittance_rows(g, s, T, PeerTables{}, 0, g.sz.t_h, stream);
+                                 cudaStream_t stream, const PasSpectrum* rgb, float* rgba) {
+  RgbExtinction e{};
+  if (rgb != nullptr && rgba != nullptr) {
+    for (int c = 0; c < 3; ++c) {
+      e.beta_r[c] = rgb->beta_r[c];
+      e.beta_m_ext[c] = rgb->beta_m_ext[c];
+      e.beta_abs[c] = rgb->beta_abs[c];
+    }
+  } else {
+    rgba = nullptr;
+  }
+  const int n = g.sz.t_w * g.sz.t_h;
+  const int warps_per_block = 8;
+  transmittance_kernel<<<(n + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0,
+                         stream>>>(g, s, T, PeerTables{}, 0, g.sz.t_h, e, rgba);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_transmittance_rows(const PasGeometry& g, const PasSpectrum& s, float* T,
@@ -201,7 +225,7 @@ cudaError_t launch_transmittance_rows(const PasGeometry& g, const PasSpectrum& s
   if (n <= 0) return cudaSuccess;
   const int warps_per_block = 8;
   transmittance_kernel<<<(n + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0,
-                         stream>>>(g, s, T, mirrors, j_begin, j_end);
+                         stream>>>(g, s, T, mirrors, j_begin, j_end, RgbExtinction{}, nullptr);
   return cudaGetLastError();
 }
 

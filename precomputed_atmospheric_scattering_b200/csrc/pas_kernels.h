@@ -42,8 +42,14 @@ struct LayerSet {
 
 // T[c][j][i] = transmittance to the top boundary (ComputeTransmittanceToTopAtmosphereBoundaryTexture,
 // functions.glsl:454-463). One warp per texel, 501 samples split across lanes, fp64.
+// With `rgb` / `rgba`, the same launch also fills the final RGBA32F transmittance texture for the
+// three channels of `rgb` (the optical lengths are wavelength independent).
+struct RgbExtinction {
+  double beta_r[3], beta_m_ext[3], beta_abs[3];
+};
 cudaError_t launch_transmittance(const PasGeometry& g, const PasSpectrum& s, float* T,
-                                 cudaStream_t stream);
+                                 cudaStream_t stream, const PasSpectrum* rgb = nullptr,
+                                 float* rgba = nullptr);
 // Rows [j_begin, j_end) only, stored to T and to its mirrors (multi-GPU: one band of rows per rank).
 cudaError_t launch_transmittance_rows(const PasGeometry& g, const PasSpectrum& s, float* T,
                                       const PeerTables& mirrors, int j_begin, int j_end,

@@ -186,6 +186,33 @@ struct BufferPool {
     cudaSetDevice(current);
   }
 };
+// Streams and events are recycled the same way (creating and destroying two streams and two events
+// per Model costs more than the pool lookup of all its buffers).
+struct StreamSet {
+  cudaStream_t stream = nullptr, aux = nullptr;
+  cudaEvent_t ev_main = nullptr, ev_aux = nullptr;
+};
+struct StreamPool {
+  std::mutex mu;
+  std::multimap<int, StreamSet> free_list;
+  bool take(int device, StreamSet* out) {
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = free_list.find(device);
+    if (it == free_list.end()) return false;
+    *out = it->second;
+    free_list.erase(it);
+    return true;
+  }
+  void give(int device, const StreamSet& s) {
+    std::lock_guard<std::mutex> lock(mu);
+    free_list.insert({device, s});
+  }
+};
+StreamPool& stream_pool() {
+  static StreamPool* p = new StreamPool();  // intentionally leaked, like the buffer pool
+  return *p;
+}
+
 BufferPool& pool() {
   static BufferPool* p = new BufferPool();  // intentionally leaked: outlives the CUDA context teardown
   return *p;
@@ -298,6 +325,7 @@ struct pas_model {
   std::vector<std::pair<std::string, float>> timings;
   PhaseMarks pending;               // events of an Init that has been enqueued but not waited for
   bool in_flight = false;
+  bool fuse_rgb_transmittance = false;  // set by Init: the first transmittance launch also fills T_rgba
   int launches = 0;
   // ---- multi-GPU ----
   int rank = 0, world = 1;
@@ -599,6 +627,8 @@ pas_status run_phase(pas_model* m, int gi, int phase, int order, bool accumulate
         PAS_CUDA(pas::launch_transmittance_rows(g, sp, m->T.f(), mirrors, j0, j1, stream));
         pas_status st = peer_barrier(m, channel, stream);
         if (st != PAS_OK) return st;
+      } else if (m->fuse_rgb_transmittance && gi == 0) {
+        PAS_CUDA(pas::launch_transmittance(g, sp, m->T.f(), stream, &m->rgb_spectrum, m->T_rgba.f()));
       } else {
         PAS_CUDA(pas::launch_transmittance(g, sp, m->T.f(), stream));
       }
@@ -813,18 +843,28 @@ pas_status pas_model_create(const pas_model_params* p, pas_model** out) {
   } else {
     PAS_CUDA(cudaGetDevice(&m->device));
   }
-  PAS_CUDA(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
   {
-    // the side stream gets the higher priority: its small kernels (1024 blocks) are scheduled as
-    // soon as the big pass running beside them frees a slot
-    int lo = 0, hi = 0;
-    PAS_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-    PAS_CUDA(cudaStreamCreateWithPriority(&m->aux, cudaStreamNonBlocking, hi));
-    PAS_CUDA(cudaEventCreateWithFlags(&m->ev_main, cudaEventDisableTiming));
-    PAS_CUDA(cudaEventCreateWithFlags(&m->ev_aux, cudaEventDisableTiming));
+    StreamSet ss;
+    if (!stream_pool().take(m->device, &ss)) {
+      // the side stream gets the higher priority: its small kernels (1024 blocks) are scheduled as
+      // soon as the big pass running beside them frees a slot
+      int lo = 0, hi = 0;
+      PAS_CUDA(cudaStreamCreateWithFlags(&ss.stream, cudaStreamNonBlocking));
+      PAS_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+      PAS_CUDA(cudaStreamCreateWithPriority(&ss.aux, cudaStreamNonBlocking, hi));
+      PAS_CUDA(cudaEventCreateWithFlags(&ss.ev_main, cudaEventDisableTiming));
+      PAS_CUDA(cudaEventCreateWithFlags(&ss.ev_aux, cudaEventDisableTiming));
+    }
+    m->stream = ss.stream;
+    m->aux = ss.aux;
+    m->ev_main = ss.ev_main;
+    m->ev_aux = ss.ev_aux;
   }
   st = allocate(m.get());
-  if (st != PAS_OK) return st;
+  if (st != PAS_OK) {
+    pas_model_destroy(m.release());  // returns the streams and whatever was allocated to the pools
+    return st;
+  }
   *out = m.release();
   return PAS_OK;
 }
@@ -832,17 +872,18 @@ pas_status pas_model_create(const pas_model_params* p, pas_model** out) {
 void pas_model_destroy(pas_model* m) {
   if (m == nullptr) return;
   cudaSetDevice(m->device);
-  if (m->stream) {
-    cudaStreamSynchronize(m->stream);
-  }
   for (auto& mk : m->pending.marks) cudaEventDestroy(mk.second);
-  if (m->aux) {
-    cudaStreamSynchronize(m->aux);
-    cudaStreamDestroy(m->aux);
+  if (m->stream) {
+    // everything enqueued by this model has to finish before its buffers go back to the pool
+    cudaStreamSynchronize(m->stream);
+    if (m->aux) cudaStreamSynchronize(m->aux);
+    StreamSet ss;
+    ss.stream = m->stream;
+    ss.aux = m->aux;
+    ss.ev_main = m->ev_main;
+    ss.ev_aux = m->ev_aux;
+    stream_pool().give(m->device, ss);
   }
-  if (m->ev_main) cudaEventDestroy(m->ev_main);
-  if (m->ev_aux) cudaEventDestroy(m->ev_aux);
-  if (m->stream) cudaStreamDestroy(m->stream);
   delete m;
 }
 
@@ -894,14 +935,18 @@ pas_status pas_model_init_async(pas_model* m, unsigned int num_scattering_orders
   };
   PhaseTimer timer(m);
   timer.mark("start");
-  if (m->num_precomputed_wavelengths > 3) {
-    // final transmittance at 680/550/440 nm (model.cc:951-963): independent of everything else
+  // final transmittance at 680/550/440 nm (model.cc:951-963). One GPU: filled by the transmittance
+  // launch of the first channel group (same optical lengths). Peer worlds compute the transmittance
+  // in bands of rows, so there the RGB table is a launch of its own, beside everything else.
+  const bool fused_rgb = m->num_precomputed_wavelengths > 3 && !m->peer;
+  if (m->num_precomputed_wavelengths > 3 && !fused_rgb) {
     PAS_CUDA(side_after_main());
     PAS_CUDA(pas::launch_transmittance(m->geom, m->rgb_spectrum, m->T_rgb.f(), side));
     PAS_CUDA(pas::launch_pack_rgba(m->T_rgb.f(), (int)m->n_t(), 3, m->T_rgba.f(), side));
     m->launches += 2;
     if (!overlap) timer.mark("final_transmittance");
   }
+  m->fuse_rgb_transmittance = fused_rgb;
   for (size_t gi = 0; gi < m->groups.size(); ++gi) {
     const bool blend = gi > 0;  // additive blending for batches after the first (model.cc:946-948)
     const int nc = m->groups[gi].nc, off = m->group_offset[gi];

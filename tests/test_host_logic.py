@@ -94,3 +94,24 @@ def test_luminance_matrices_match_the_reference_header(pas):
     spec = pas.earth(3)
     rgb = pas.convert_spectrum_to_linear_srgb(spec.wavelengths, spec.solar_irradiance)
     assert np.allclose(rgb, gold["solar_srgb"], rtol=1e-12)
+
+
+def test_ensemble_sweep_is_a_seeded_grid(pas):
+    """BASELINE config 5: 64 atmospheres = turbidity x ozone x albedo; same seed, same atmospheres;
+    the axes vary what the demo's keys vary (demo.cc:208-234) and nothing else."""
+    a, b = pas.ensemble.sweep(), pas.ensemble.sweep()
+    assert len(a) == 64
+    key = lambda s: (s.mie_density[0].exp_scale, s.absorption_extinction[10], s.ground_albedo[0])
+    assert [key(s) for s in a] == [key(s) for s in b]
+    assert len({key(s) for s in a}) == 64
+    assert [key(s) for s in pas.ensemble.sweep(seed=1)] != [key(s) for s in a]
+    plain = pas.ensemble.sweep(2, 2, 2, jitter=0.0)
+    assert len(plain) == 8
+    heights = sorted({round(-1.0 / s.mie_density[0].exp_scale) for s in plain})
+    assert heights == [800, 1200]
+    base = pas.earth(3)
+    for s in a:
+        assert s.rayleigh_scattering == base.rayleigh_scattering and s.solar_irradiance == base.solar_irradiance
+        assert 0.0 <= s.ground_albedo[0] <= 1.0
+    with pytest.raises(ValueError):
+        pas.ensemble.sweep(5, 1, 1)
