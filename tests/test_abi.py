@@ -104,3 +104,34 @@ def test_last_error_is_thread_local_string(pas):
     lib = pas.load_library()
     assert lib.pas_model_init(None, 4) == 1
     assert b"NULL" in lib.pas_last_error()
+
+
+def test_null_handles_are_rejected_everywhere(pas):
+    """Every entry point that takes a model validates it before touching CUDA: status 1
+    (PAS_ERR_INVALID_ARGUMENT) and a message, never a crash -- also without a GPU."""
+    import ctypes
+    lib = pas.load_library()
+    n = ctypes.c_size_t(0)
+    buf = ctypes.create_string_buffer(pas.model.IPC_EXPORT_BYTES)
+    calls = [
+        lambda: lib.pas_model_init(None, 4),
+        lambda: lib.pas_model_init_async(None, 4),
+        lambda: lib.pas_model_wait(None),
+        lambda: lib.pas_model_ipc_export(None, 0, 2, buf, ctypes.byref(n)),
+        lambda: lib.pas_model_attach_peers(None, buf, pas.model.IPC_EXPORT_BYTES),
+        lambda: lib.pas_model_attach_world(None, 0, 2, None),
+        lambda: lib.pas_model_save_dat(None, b"/tmp"),
+        lambda: lib.pas_model_set_capture(None, 1),
+    ]
+    for call in calls:
+        assert call() == 1
+        assert len(lib.pas_last_error()) > 0
+    lib.pas_model_destroy(None)  # a no-op, like free(NULL)
+
+
+def test_ipc_export_size_contract(pas):
+    """include/pas_b200.h: PAS_IPC_EXPORT_BYTES is what pas_model_ipc_export writes per rank and what
+    world.py all-gathers; the Python mirror and the header must agree."""
+    text = open(HEADER).read()
+    m = re.search(r"#define\s+PAS_IPC_EXPORT_BYTES\s+(\d+)", text)
+    assert m and int(m.group(1)) == pas.model.IPC_EXPORT_BYTES
