@@ -53,7 +53,9 @@ indirect_irradiance_kernel(const __grid_constant__ PasGeometry g,
   }
   __syncthreads();
 
-  // stage: reduce (r, mu, mu_s) once per (ring, channel, slab)
+  // stage: reduce (r, mu, mu_s) once per (ring, channel, slab); unrolled so that the 8 corner loads of
+  // several items are in flight together (the kernel is one wave of latency-bound blocks)
+#pragma unroll 4
   for (int idx = tid; idx < NT * PAS_IRR_THETA * NC * nu_n; idx += kThreads) {
     const int c = idx % NC, s = (idx / NC) % nu_n, l = (idx / (nu_n * NC)) % PAS_IRR_THETA;
     const int t = idx / (nu_n * NC * PAS_IRR_THETA);

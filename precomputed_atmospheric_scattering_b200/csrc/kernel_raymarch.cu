@@ -108,11 +108,17 @@ __device__ __forceinline__ void fill_sample(const PasGeometry& g, double d, doub
   *out = s;
 }
 
-template <int NC, typename Sample>
-__device__ void ray_sample_setup(const PasGeometry& g, const float* __restrict__ T, double r,
-                                 double rho, double mu, bool hit, double d_end, int i,
-                                 Sample* out, float* Tw) {
-  constexpr int CP = PAS_CHANNEL_PITCH(NC);
+// Transmittance taps of one sample: GetTransmittance(r, mu, d_i, hit) is the ratio of two bilinear
+// fetches (functions.glsl:493-519); the taps are channel independent, the fetches are not.
+struct PathTaps {
+  Tap ax, ay, bx, by;
+  double w;  // trapezoid weight * dx
+};
+
+// Phase A, step 1: one thread per sample (fp64 geometry): the per-sample record and the taps.
+template <typename Sample>
+__device__ void ray_sample_geometry(const PasGeometry& g, double r, double rho, double mu, bool hit,
+                                    double d_end, int i, Sample* out, PathTaps* taps) {
   const double dx = d_end / PAS_RAY_SAMPLES;
   const double d = i * dx;
   const double r_i = d_clamp(sqrt(d * d + 2.0 * r * mu * d + r * r), g.bottom, g.top);
@@ -128,16 +134,33 @@ __device__ void ray_sample_setup(const PasGeometry& g, const float* __restrict__
     transmittance_xy(g, r, mu, &xa, &ya);
     transmittance_xy(g, r_i, mu_i, &xb, &yb);
   }
-  const Tap ax = make_tap(xa, g.sz.t_w), ay = make_tap(ya, g.sz.t_h);
-  const Tap bx = make_tap(xb, g.sz.t_w), by = make_tap(yb, g.sz.t_h);
-  const double w = ((i == 0 || i == PAS_RAY_SAMPLES) ? 0.5 : 1.0) * dx;
-#pragma unroll 1
-  for (int c = 0; c < NC; ++c) {
-    const double t = fmin(fetch_t(T, CP, c, g.sz.t_w, ax, ay) / fetch_t(T, CP, c, g.sz.t_w, bx, by), 1.0);
-    Tw[c] = (float)(t * w);
+  PathTaps t;
+  t.ax = make_tap(xa, g.sz.t_w);
+  t.ay = make_tap(ya, g.sz.t_h);
+  t.bx = make_tap(xb, g.sz.t_w);
+  t.by = make_tap(yb, g.sz.t_h);
+  t.w = ((i == 0 || i == PAS_RAY_SAMPLES) ? 0.5 : 1.0) * dx;
+  *taps = t;
+}
+
+// Phase A, step 2: all threads, one (sample, channel) pair each:
+// Tw[i][c] = T(r, mu, d_i)[c] * trapezoid weight * dx. (A sample thread doing its NC channels one
+// after the other kept the other 200 threads of the block waiting on ~15 dependent L2 round trips.)
+template <int NC>
+__device__ __forceinline__ void ray_sample_transmittance(const PasGeometry& g, const float* __restrict__ T,
+                                                         const PathTaps* taps, float (*Tw)[PAS_CHANNEL_PITCH(NC)],
+                                                         int tid, int nthreads) {
+  constexpr int CP = PAS_CHANNEL_PITCH(NC);
+  for (int idx = tid; idx < kSamples * CP; idx += nthreads) {
+    const int i = idx / CP, c = idx % CP;
+    float v = 0.f;
+    if (c < NC) {
+      const PathTaps& p = taps[i];
+      const double t = fmin(fetch_t(T, CP, c, g.sz.t_w, p.ax, p.ay) / fetch_t(T, CP, c, g.sz.t_w, p.bx, p.by), 1.0);
+      v = (float)(t * p.w);
+    }
+    Tw[i][c] = v;
   }
-#pragma unroll
-  for (int c = NC; c < CP; ++c) Tw[c] = 0.f;
 }
 
 // RGBA store / accumulate into a final table (fp32 or fp16 texels).
@@ -229,10 +252,13 @@ multiple_scattering_kernel(const __grid_constant__ PasGeometry g,
   float4* sRow = reinterpret_cast<float4*>(smem_dyn);  // [2][Q * pitch]
   const float4* dJ4 = reinterpret_cast<const float4*>(dJ);
 
+  __shared__ PathTaps sTaps[kSamples];
   const BlockRay ray = block_ray(g, k, j);
   if (tid < kSamples) {
-    ray_sample_setup<NC>(g, T, ray.r, ray.rho, ray.mu, ray.hit, ray.d_end, tid, &sSample[tid], sTw[tid]);
+    ray_sample_geometry(g, ray.r, ray.rho, ray.mu, ray.hit, ray.d_end, tid, &sSample[tid], &sTaps[tid]);
   }
+  __syncthreads();
+  ray_sample_transmittance<NC>(g, T, sTaps, sTw, tid, (int)blockDim.x);
 
   // per-thread axes: mu_s (column) and nu (slab)
   const int x = tid;  // one block covers the whole row; threads >= width only help phase A
@@ -379,9 +405,10 @@ multiple_scattering_rows_kernel(const __grid_constant__ PasGeometry g,
   float4* sRow = reinterpret_cast<float4*>(smem_dyn);  // [2][Q * pitch]
   const float4* dJ4 = reinterpret_cast<const float4*>(dJ);
 
+  __shared__ PathTaps sTaps[kSamples];
   const BlockRay ray = block_ray(g, k, j);
   if (tid < kSamples) {
-    ray_sample_setup<NC>(g, T, ray.r, ray.rho, ray.mu, ray.hit, ray.d_end, tid, &sSample[tid], sTw[tid]);
+    ray_sample_geometry(g, ray.r, ray.rho, ray.mu, ray.hit, ray.d_end, tid, &sSample[tid], &sTaps[tid]);
   }
 
   // ---- permutation: texels with nu on a slab first ---------------------------------------------
@@ -406,6 +433,8 @@ multiple_scattering_rows_kernel(const __grid_constant__ PasGeometry g,
     const int pos = on_slab ? before + rank_in_warp : total + (warp * 32 - before) + (lane - rank_in_warp);
     sPerm[pos] = tid;
   }
+  // (the barrier inside the permutation published the taps of phase A)
+  ray_sample_transmittance<NC>(g, T, sTaps, sTw, tid, WIDTH);
   // ---- slot plan ---------------------------------------------------------------------------------
   // Row (layer k, mu row j) always lives in slot 2 (k & 1) + (j & 1): the four corner rows of a sample
   // fall in four different slots, and a row shared with the previous sample is found where it was.
@@ -589,10 +618,13 @@ single_scattering_kernel(const __grid_constant__ PasGeometry g,
   float4* sRow = reinterpret_cast<float4*>(smem_dyn);  // [2][Q * pitch]
   const float4* T4 = reinterpret_cast<const float4*>(T);
 
+  __shared__ PathTaps sTaps[kSamples];
   const BlockRay ray = block_ray(g, k, j);
   if (tid < kSamples) {
-    ray_sample_setup<NC>(g, T, ray.r, ray.rho, ray.mu, ray.hit, ray.d_end, tid, &sSample[tid], sTw[tid]);
+    ray_sample_geometry(g, ray.r, ray.rho, ray.mu, ray.hit, ray.d_end, tid, &sSample[tid], &sTaps[tid]);
   }
+  __syncthreads();
+  ray_sample_transmittance<NC>(g, T, sTaps, sTw, tid, (int)blockDim.x);
   const int x = NU_LANES ? (tid % nu_n) * mu_s_n + tid / nu_n : tid;
   const bool active = x < width;
   const int i_nu = active ? x / mu_s_n : 0, i_mu_s = active ? x % mu_s_n : 0;
