@@ -232,7 +232,11 @@ pas_status pas_spectral_channels(unsigned int num_precomputed_wavelengths, int* 
 
 /* When enabled, Init keeps a device copy of every intermediate (planar per channel, texel order
  * x fastest): "transmittance", "delta_irradiance_<n>", "delta_rayleigh", "delta_mie",
- * "delta_density_<n>", "delta_multiple_<n>". Costs memory and time; off by default. */
+ * "delta_density_<n>", "delta_multiple_<n>". Costs memory and time; off by default. With captures
+ * Init enqueues every pass on one stream in the reference's order; without, it overlaps the
+ * irradiance passes with the multiple-scattering passes and reuses the delta_rayleigh buffer for
+ * odd orders, so the live buffers below are only meaningful after single passes or captured runs
+ * (the products are bit-identical either way). */
 pas_status pas_model_set_capture(pas_model* model, int enabled);
 /* num_floats: in = capacity of dst, out = floats needed/copied. dst may be NULL to query. */
 pas_status pas_model_read_intermediate(pas_model* model, const char* name, float* dst,

@@ -7,17 +7,22 @@
 // texels of a block share the ray (r, mu): the 51 sample points, their radii, the transmittance
 // along the ray and the (r, mu) interpolation footprint in the source table are identical for
 // every thread. So per sample:
-//   phase A (once per block, 51 threads, fp64): sample geometry, path transmittance per channel,
-//           table taps of the shared axes;
+//   phase A (once per block, fp64): 51 threads compute the sample geometry and the table taps of
+//           the shared axes; then all threads compute the path transmittance, one (sample, channel)
+//           pair each;
 //   stage   (all threads): the shared-axis interpolation is applied ONCE to a whole table row:
 //           the 4 (layer, row) corner rows of the channel-interleaved source table (16 KB each at
 //           15 channels, contiguous) are read with 128-bit loads from L2, combined in registers
 //           and written to shared memory as one row of texels (multiple scattering); the 2
-//           transmittance rows bracketing r_i likewise (single scattering);
+//           transmittance rows bracketing r_i likewise (single scattering). At the reference's row
+//           width the corner rows live in register slots across samples: rows shared with the
+//           previous sample are not read again, the next sample's rows are prefetched;
 //   consume (per thread, fp32): only the thread-dependent axes remain (mu_s and nu, resp. the
-//           sun-direction mu): 2-4 texel reads (128-bit, XOR-swizzled so that neighbouring
-//           texels fall in different banks) instead of 16 L2 gathers per channel.
-// The stage buffer is double buffered: one __syncthreads per sample.
+//           sun-direction mu): 2-4 texel reads (128-bit) instead of 16 L2 gathers per channel.
+// The stage buffer is double buffered: one __syncthreads per sample. Three kernels:
+// multiple_scattering_rows_kernel (row width 256, more than 4 channels: the bench path),
+// multiple_scattering_kernel (any width; also 256 with <= 4 channels, where a row is only 4 KB),
+// single_scattering_kernel (both).
 #include "pas_kernels.h"
 #include "pas_physics.cuh"
 
