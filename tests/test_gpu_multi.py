@@ -72,3 +72,60 @@ def test_two_gpus_match_one(tmp_path, pas, full_size, exchange):
             assert np.allclose(got["S"], S, rtol=2e-6, atol=1e-7 * np.abs(S).max())
             assert np.allclose(got["E"], E, rtol=1e-5, atol=1e-7 * np.abs(E).max())
     single.close()
+
+
+def _variant_worker(rank, world_size, port, out_dir):
+    import torch.distributed as dist
+
+    import precomputed_atmospheric_scattering_b200 as pas
+    from precomputed_atmospheric_scattering_b200 import world
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world_size,
+                            device_id=torch.device("cuda", rank))
+    try:
+        for name, spec, orders in _variants(pas):
+            model = pas.Model.from_spec(spec, device=rank, sizes=SIZES)
+            world.attach(model, exchange="peer")
+            model.Init(orders)
+            out = dict(S=model.scattering, E=model.irradiance, T=model.transmittance)
+            if not spec.combine_scattering_textures:
+                out["M"] = model.single_mie_scattering
+            np.savez(os.path.join(out_dir, f"{name}_rank{rank}.npz"), **out)
+            model.close()
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def _variants(pas):
+    """Paths of the peer exchange the Earth runs above do not take: a separate single-Mie table with
+    fp16 products (second final push), 24 channels = two launch groups (the buffer parity carries
+    over from one group to the next), and Init(1) (no order loop: only the final exchange)."""
+    sep = pas.small_planet()
+    sep.combine_scattering_textures, sep.half_precision = False, True
+    wide = pas.small_planet()
+    wide.num_precomputed_wavelengths = 24
+    return [("separate_mie_fp16", sep, 3), ("two_groups", wide, 3), ("single_order", pas.small_planet(), 1)]
+
+
+@pytest.mark.timeout(600)
+def test_peer_exchange_variants(tmp_path, pas):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    import torch.multiprocessing as mp
+    mp.spawn(_variant_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    for name, spec, orders in _variants(pas):
+        single = pas.Model.from_spec(spec, device=0, sizes=SIZES)
+        single.Init(orders)
+        want = dict(S=single.scattering, E=single.irradiance, T=single.transmittance)
+        if not spec.combine_scattering_textures:
+            want["M"] = single.single_mie_scattering
+        for rank in range(2):
+            got = np.load(os.path.join(tmp_path, f"{name}_rank{rank}.npz"))
+            for key, ref in want.items():
+                ref = np.asarray(ref, dtype=np.float64)
+                tol = 2e-3 if spec.half_precision and key in ("S", "M") else 2e-6
+                assert np.allclose(np.asarray(got[key], dtype=np.float64), ref, rtol=tol,
+                                   atol=1e-6 * np.abs(ref).max()), (name, rank, key)
+        single.close()
