@@ -119,6 +119,15 @@ pas_status pas_model_init(pas_model* model, unsigned int num_scattering_orders);
  * for its Init first. */
 pas_status pas_model_init_async(pas_model* model, unsigned int num_scattering_orders);
 pas_status pas_model_wait(pas_model* model);
+/* Pipelined read-back for callers that upload the tables right after Init (the GL upload of
+ * atmosphere/model.cc:747-766, the .dat export of demo/webgl/precompute.cc:85-106): registers host
+ * destinations (NULL = not wanted; native texel format and size of pas_model_texture_info, i.e. what
+ * pas_model_read_texture(as_float32 = 0) returns; page-locked memory for the copies to overlap).
+ * Every later Init copies each table out as soon as its last writer is done -- T after the first
+ * pass, the scattering table in bands of layers behind the last multiple-scattering pass -- and the
+ * buffers are valid when pas_model_init / pas_model_wait returns. Pass four NULLs to unregister. */
+pas_status pas_model_set_host_outputs(pas_model* model, void* transmittance, void* scattering,
+                                      void* single_mie, void* irradiance);
 
 pas_status pas_model_texture_info(const pas_model* model, pas_texture which,
                                   pas_texture_info* info);

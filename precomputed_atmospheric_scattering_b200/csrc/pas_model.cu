@@ -189,8 +189,8 @@ struct BufferPool {
 // Streams and events are recycled the same way (creating and destroying two streams and two events
 // per Model costs more than the pool lookup of all its buffers).
 struct StreamSet {
-  cudaStream_t stream = nullptr, aux = nullptr;
-  cudaEvent_t ev_main = nullptr, ev_aux = nullptr;
+  cudaStream_t stream = nullptr, aux = nullptr, copy = nullptr;
+  cudaEvent_t ev_main = nullptr, ev_aux = nullptr, ev_copy = nullptr;
 };
 struct StreamPool {
   std::mutex mu;
@@ -315,6 +315,11 @@ struct pas_model {
   cudaStream_t stream = nullptr;
   cudaStream_t aux = nullptr;       // side stream of Init: irradiance passes, final RGB transmittance
   cudaEvent_t ev_main = nullptr, ev_aux = nullptr;
+  // host destinations registered with pas_model_set_host_outputs: Init copies every product table
+  // out as soon as it is final, on a copy stream beside the passes still running
+  cudaStream_t copy = nullptr;
+  cudaEvent_t ev_copy = nullptr;
+  void* host_out[4] = {nullptr, nullptr, nullptr, nullptr};  // indexed by pas_texture
   DeviceBuffer T, dE, dR, dM, dJ, dS, dirs, G, cR, cM, T_rgb, scratch;
   DeviceBuffer S, M, E, T_rgba;
   DeviceBuffer render_in[4], render_out[2];  // staging of host-pointer render queries
@@ -607,10 +612,10 @@ pas_status peer_barrier(pas_model* m, int channel, cudaStream_t stream) {
 // pass writes. The reference aliases both to one texture (model.cc:897); Init alternates two buffers
 // so that the irradiance pass of order n can overlap the multiple-scattering pass of order n.
 pas_status run_phase(pas_model* m, int gi, int phase, int order, bool accumulate, cudaStream_t stream,
-                     float* ds_in, float* ds_out, int channel = 0) {
+                     float* ds_in, float* ds_out, int channel = 0, const pas::LayerSet* only = nullptr) {
   const PasSpectrum& sp = m->groups[gi];
   const PasGeometry& g = m->geom;
-  const pas::LayerSet ks = m->layers();
+  const pas::LayerSet ks = only != nullptr ? *only : m->layers();
   const int k0 = ks.begin;
   pas::FinalTables fin = final_tables(m, accumulate);
   switch (phase) {
@@ -854,8 +859,12 @@ pas_status pas_model_create(const pas_model_params* p, pas_model** out) {
       PAS_CUDA(cudaStreamCreateWithPriority(&ss.aux, cudaStreamNonBlocking, hi));
       PAS_CUDA(cudaEventCreateWithFlags(&ss.ev_main, cudaEventDisableTiming));
       PAS_CUDA(cudaEventCreateWithFlags(&ss.ev_aux, cudaEventDisableTiming));
+      PAS_CUDA(cudaStreamCreateWithFlags(&ss.copy, cudaStreamNonBlocking));
+      PAS_CUDA(cudaEventCreateWithFlags(&ss.ev_copy, cudaEventDisableTiming));
     }
     m->stream = ss.stream;
+    m->copy = ss.copy;
+    m->ev_copy = ss.ev_copy;
     m->aux = ss.aux;
     m->ev_main = ss.ev_main;
     m->ev_aux = ss.ev_aux;
@@ -877,7 +886,10 @@ void pas_model_destroy(pas_model* m) {
     // everything enqueued by this model has to finish before its buffers go back to the pool
     cudaStreamSynchronize(m->stream);
     if (m->aux) cudaStreamSynchronize(m->aux);
+    if (m->copy) cudaStreamSynchronize(m->copy);
     StreamSet ss;
+    ss.copy = m->copy;
+    ss.ev_copy = m->ev_copy;
     ss.stream = m->stream;
     ss.aux = m->aux;
     ss.ev_main = m->ev_main;
@@ -890,6 +902,20 @@ void pas_model_destroy(pas_model* m) {
 pas_status pas_model_init(pas_model* m, unsigned int num_scattering_orders) {
   pas_status st = pas_model_init_async(m, num_scattering_orders);
   return st != PAS_OK ? st : pas_model_wait(m);
+}
+
+pas_status pas_model_set_host_outputs(pas_model* m, void* transmittance, void* scattering, void* single_mie,
+                                      void* irradiance) {
+  if (m == nullptr) return fail(PAS_ERR_INVALID_ARGUMENT, "model is NULL");
+  { pas_status settled = settle(m); if (settled != PAS_OK) return settled; }
+  if (single_mie != nullptr && m->combined) {
+    return fail(PAS_ERR_STATE, "this model has no single-Mie table (combined scattering textures)");
+  }
+  m->host_out[PAS_TEXTURE_TRANSMITTANCE] = transmittance;
+  m->host_out[PAS_TEXTURE_SCATTERING] = scattering;
+  m->host_out[PAS_TEXTURE_SINGLE_MIE] = single_mie;
+  m->host_out[PAS_TEXTURE_IRRADIANCE] = irradiance;
+  return PAS_OK;
 }
 
 pas_status pas_model_wait(pas_model* m) {
@@ -933,6 +959,25 @@ pas_status pas_model_init_async(pas_model* m, unsigned int num_scattering_orders
     cudaError_t e = cudaEventRecord(m->ev_aux, side);
     return e != cudaSuccess ? e : cudaStreamWaitEvent(main, m->ev_aux, 0);
   };
+  // Pipelined read-back (pas_model_set_host_outputs; one GPU, no captures): a table is copied to the
+  // host as soon as its last writer is done -- T after the first pass, the single-Mie table after
+  // single scattering, E after the last irradiance pass, S in four bands of layers behind the four
+  // launches the last multiple-scattering pass is split into.
+  const bool pipe_out = !m->capture && m->world == 1 &&
+                        (m->host_out[0] || m->host_out[1] || m->host_out[2] || m->host_out[3]);
+  auto copy_after = [&](cudaStream_t producer, int which, size_t offset, size_t bytes) -> cudaError_t {
+    if (m->host_out[which] == nullptr || bytes == 0) return cudaSuccess;
+    const DeviceBuffer* buf = nullptr;
+    pas_texture_info info;
+    if (texture_lookup(m, (pas_texture)which, &buf, &info) != PAS_OK || !info.present) return cudaSuccess;
+    cudaError_t e = cudaEventRecord(m->ev_copy, producer);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(m->copy, m->ev_copy, 0);
+    if (e == cudaSuccess) {
+      e = cudaMemcpyAsync(static_cast<char*>(m->host_out[which]) + offset, static_cast<const char*>(buf->p) + offset,
+                          bytes, cudaMemcpyDeviceToHost, m->copy);
+    }
+    return e;
+  };
   PhaseTimer timer(m);
   timer.mark("start");
   // final transmittance at 680/550/440 nm (model.cc:951-963). One GPU: filled by the transmittance
@@ -953,12 +998,27 @@ pas_status pas_model_init_async(pas_model* m, unsigned int num_scattering_orders
     pas_status st;
     float* const dS = m->dS.f();
     if ((st = run_phase(m, (int)gi, 0, 0, blend, main, dS, dS)) != PAS_OK) return st;
+    if (gi == 0 && m->num_precomputed_wavelengths <= 3) {
+      PAS_CUDA(pas::launch_pack_rgba(m->T.f(), (int)m->n_t(), 3, m->T_rgba.f(), main));
+      m->launches += 1;
+    }
+    if (pipe_out && gi == 0 && (fused_rgb || m->num_precomputed_wavelengths <= 3)) {
+      PAS_CUDA(copy_after(main, PAS_TEXTURE_TRANSMITTANCE, 0, m->n_t() * 16));
+    }
     timer.mark("transmittance");
     if ((st = capture_copy(m, "transmittance", m->T.f(), m->n_t(), nc, off, true)) != PAS_OK) return st;
     if ((st = run_phase(m, (int)gi, 1, 0, blend, main, dS, dS)) != PAS_OK) return st;
     timer.mark("direct_irradiance");
     if ((st = capture_copy(m, "delta_irradiance_1", m->dE.f(), m->n_e(), nc, off, false)) != PAS_OK) return st;
     if ((st = run_phase(m, (int)gi, 2, 0, blend, main, dS, dS)) != PAS_OK) return st;
+    const bool last_group = gi + 1 == m->groups.size();
+    if (pipe_out && last_group) {
+      // the single-Mie table is written by single scattering only (model.cc:151-156)
+      PAS_CUDA(copy_after(main, PAS_TEXTURE_SINGLE_MIE, 0, m->n_s() * m->s_texel_bytes()));
+      if (num_scattering_orders == 1) {
+        PAS_CUDA(copy_after(main, PAS_TEXTURE_SCATTERING, 0, m->n_s() * m->s_texel_bytes()));
+      }
+    }
     timer.mark("single_scattering");
     if ((st = capture_copy(m, "delta_rayleigh", m->dR.f(), m->n_s(), nc, off, true)) != PAS_OK) return st;
     if ((st = capture_copy(m, "delta_mie", m->dM.f(), m->n_s(), nc, off, true)) != PAS_OK) return st;
@@ -980,7 +1040,20 @@ pas_status pas_model_init_async(pas_model* m, unsigned int num_scattering_orders
       if ((st = capture_copy(m, "delta_irradiance_" + tag, m->dE.f(), m->n_e(), nc, off, false)) != PAS_OK) return st;
       // (multi-GPU: the density table is complete once the exchange of phase 3 / 4 is done)
       if ((st = capture_copy(m, "delta_density_" + tag, m->cur_dJ(), m->n_s(), nc, off, true)) != PAS_OK) return st;
-      if ((st = run_phase(m, (int)gi, 5, (int)order, blend, main, ds_in, ds_out)) != PAS_OK) return st;
+      if (pipe_out && last_group && order == num_scattering_orders) {
+        // E is final (side stream); S becomes final band by band
+        PAS_CUDA(copy_after(side, PAS_TEXTURE_IRRADIANCE, 0, m->n_e() * 16));
+        const int r_n = m->geom.sz.r_n, parts = r_n >= 8 ? 4 : 1;
+        const size_t layer_bytes = m->layer_texels() * m->s_texel_bytes();
+        for (int part = 0; part < parts; ++part) {
+          const pas::LayerSet band{part * r_n / parts, (part + 1) * r_n / parts, 1};
+          if ((st = run_phase(m, (int)gi, 5, (int)order, blend, main, ds_in, ds_out, 0, &band)) != PAS_OK) return st;
+          PAS_CUDA(copy_after(main, PAS_TEXTURE_SCATTERING, (size_t)band.begin * layer_bytes,
+                              (size_t)band.count() * layer_bytes));
+        }
+      } else if ((st = run_phase(m, (int)gi, 5, (int)order, blend, main, ds_in, ds_out)) != PAS_OK) {
+        return st;
+      }
       timer.mark("multiple_scattering_" + tag);
       if ((st = capture_copy(m, "delta_multiple_" + tag, ds_out, m->n_s(), nc, off, true)) != PAS_OK) return st;
       ds_in = ds_out;
@@ -988,9 +1061,14 @@ pas_status pas_model_init_async(pas_model* m, unsigned int num_scattering_orders
     // the next group restarts with the transmittance pass, which the side stream may still read
     PAS_CUDA(main_after_side());
   }
-  if (m->num_precomputed_wavelengths <= 3) {
-    PAS_CUDA(pas::launch_pack_rgba(m->T.f(), (int)m->n_t(), 3, m->T_rgba.f(), main));
-    m->launches += 1;
+  if (pipe_out) {
+    if (num_scattering_orders == 1) PAS_CUDA(copy_after(main, PAS_TEXTURE_IRRADIANCE, 0, m->n_e() * 16));
+    if (m->num_precomputed_wavelengths > 3 && !fused_rgb) {
+      PAS_CUDA(copy_after(main, PAS_TEXTURE_TRANSMITTANCE, 0, m->n_t() * 16));
+    }
+    // the main stream ends after the last copy: one synchronisation covers everything
+    PAS_CUDA(cudaEventRecord(m->ev_copy, m->copy));
+    PAS_CUDA(cudaStreamWaitEvent(main, m->ev_copy, 0));
   }
   if (m->world > 1 && m->peer) {
     // every rank ends with the complete scattering table(s): push this rank's layers, then barrier
@@ -1024,6 +1102,17 @@ pas_status pas_model_init_async(pas_model* m, unsigned int num_scattering_orders
                                 m->M.p, slab_bytes, ncclChar, m->comm, m->stream));
     }
     PAS_NCCL(nccl().GroupEnd());
+  }
+  if (!pipe_out) {
+    // captures or a multi-GPU world: registered host outputs are filled by plain copies at the end
+    for (int which = 0; which < 4; ++which) {
+      if (m->host_out[which] == nullptr) continue;
+      const DeviceBuffer* buf = nullptr;
+      pas_texture_info info;
+      if (texture_lookup(m, (pas_texture)which, &buf, &info) != PAS_OK || !info.present) continue;
+      const size_t bytes = (size_t)info.width * info.height * info.depth * 4 * info.bytes_per_channel;
+      PAS_CUDA(cudaMemcpyAsync(m->host_out[which], buf->p, bytes, cudaMemcpyDeviceToHost, main));
+    }
   }
   timer.mark("finalize");
   m->in_flight = true;

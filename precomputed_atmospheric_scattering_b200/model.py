@@ -96,6 +96,7 @@ def load_library() -> ctypes.CDLL:
         lib.pas_model_init.argtypes = [ctypes.c_void_p, ctypes.c_uint]
         lib.pas_model_init_async.argtypes = [ctypes.c_void_p, ctypes.c_uint]
         lib.pas_model_wait.argtypes = [ctypes.c_void_p]
+        lib.pas_model_set_host_outputs.argtypes = [ctypes.c_void_p] + [ctypes.c_void_p] * 4
         lib.pas_model_texture_info.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(_TextureInfo)]
         lib.pas_model_texture_device_ptr.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]
         lib.pas_model_read_texture.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t]
@@ -278,6 +279,26 @@ class Model:
 
     def Wait(self) -> None:
         _check(self._lib.pas_model_wait(self._h))
+
+    def set_host_outputs(self, transmittance: Optional[np.ndarray] = None, scattering: Optional[np.ndarray] = None,
+                         single_mie_scattering: Optional[np.ndarray] = None,
+                         irradiance: Optional[np.ndarray] = None) -> None:
+        """Registers host arrays (native texel format: what ``texture(which, as_float32=False)``
+        returns; pinned memory for overlap) that every later ``Init`` fills while it runs
+        (pas_model_set_host_outputs). The arrays must stay alive until they are unregistered."""
+        ptrs = []
+        for which, arr in ((TEXTURE_TRANSMITTANCE, transmittance), (TEXTURE_SCATTERING, scattering),
+                           (TEXTURE_SINGLE_MIE, single_mie_scattering), (TEXTURE_IRRADIANCE, irradiance)):
+            if arr is None:
+                ptrs.append(None)
+                continue
+            info = self.texture_info(which)
+            need = info.width * info.height * info.depth * 4 * info.bytes_per_channel
+            if not (arr.flags["C_CONTIGUOUS"] and arr.nbytes == need):
+                raise ValueError(f"host output {which}: need a contiguous array of {need} bytes")
+            ptrs.append(ctypes.c_void_p(arr.ctypes.data))
+        self._host_outputs = (transmittance, scattering, single_mie_scattering, irradiance)  # keep alive
+        _check(self._lib.pas_model_set_host_outputs(self._h, *ptrs))
 
     def GetShaderSource(self, glsl_directory: str) -> str:
         """The source atmosphere::Model::shader() compiles (atmosphere/model.cc:691-744, 769-772)."""
