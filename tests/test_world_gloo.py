@@ -36,6 +36,33 @@ def _worker(rank, world_size, port, out_dir):
         # 1b. the IPC-handle exchange of the peer path: every rank gets every blob, in rank order
         blobs = world.all_gather_bytes(bytes([rank]) * 400)
         assert blobs == b"".join(bytes([r]) * 400 for r in range(world_size))
+        # 1c. world.attach over the peer exchange: every rank exports, the blobs are all-gathered in
+        # rank order and handed to attach_peers; the NCCL exchange broadcasts rank 0's unique id
+        class FakeModel:
+            device = None
+
+            def __init__(self):
+                self.calls = []
+
+            def ipc_export(self, r, w):
+                self.calls.append(("export", r, w))
+                return bytes([10 + r]) * 464
+
+            def attach_peers(self, blob, per_rank):
+                self.calls.append(("peers", blob, per_rank))
+
+            def attach_world(self, r, w, uid):
+                self.calls.append(("world", r, w, uid))
+
+        fm = FakeModel()
+        assert world.attach(fm, exchange="peer") == (rank, world_size)
+        assert fm.calls[0] == ("export", rank, world_size)
+        assert fm.calls[1] == ("peers", b"".join(bytes([10 + r]) * 464 for r in range(world_size)), 464)
+        try:
+            world.attach(FakeModel(), exchange="carrier pigeon")
+            raise AssertionError("unknown exchange accepted")
+        except ValueError:
+            pass
         # 2. the slowest rank defines the step time
         assert world.max_over_ranks(10.0 + rank) == 10.0 + world_size - 1
         # 3. r-slab sharded density pass == single-process pass, bit for bit
