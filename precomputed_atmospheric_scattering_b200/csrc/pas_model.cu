@@ -1399,6 +1399,7 @@ pas_status pas_model_attach_world(pas_model* m, int rank, int world_size, const 
   }
   m->rank = rank;
   m->world = world_size;
+  m->peer = false;  // a model attached to an NCCL world no longer uses a peer mapping it may have had
   return PAS_OK;
 }
 

@@ -13,12 +13,14 @@ works with any torch.distributed backend (``nccl`` on the GPU box, ``gloo`` in t
 from __future__ import annotations
 
 import os
+import warnings
 from typing import Callable, List, Optional, Tuple
 
 import torch
 import torch.distributed as dist
 
 UNIQUE_ID_BYTES = 128  # PAS_NCCL_UNIQUE_ID_BYTES
+_PEER_WORLDS = set()   # (rank, world) for which this process has agreed on the peer exchange
 
 
 def slab(r_n: int, rank: int, world: int) -> Tuple[int, int]:
@@ -80,12 +82,35 @@ def attach(model, group=None, exchange: Optional[str] = None) -> Tuple[int, int]
     if world == 1:
         model.attach_world(0, 1, None)
         return rank, world
-    exchange = exchange or os.environ.get("PAS_EXCHANGE", "peer")
+    requested = exchange or os.environ.get("PAS_EXCHANGE")
+    exchange = requested or "peer"
     if exchange == "peer":
-        blob = model.ipc_export(rank, world)
-        model.attach_peers(all_gather_bytes(blob, group), len(blob))
-        return rank, world
-    if exchange != "nccl":
+        # Every rank must end up on the same exchange: a rank whose GPU cannot export or map peer
+        # memory (no P2P between the devices, IPC disabled in the container) tells the others, and
+        # unless the peer exchange was asked for explicitly all of them fall back to NCCL together.
+        if (rank, world) in _PEER_WORLDS:
+            # this process has already mapped its peers once (and so has every other rank): no need
+            # to agree again; a failure now is an error, not a reason to change the exchange
+            blob = model.ipc_export(rank, world)
+            model.attach_peers(all_gather_bytes(blob, group), len(blob))
+            return rank, world
+        blob, error = b"", None
+        try:
+            blob = model.ipc_export(rank, world)
+        except Exception as e:  # PasError
+            error = e
+        if _all_ok(error is None, group):
+            try:
+                model.attach_peers(all_gather_bytes(blob, group), len(blob))
+            except Exception as e:
+                error = e
+            if _all_ok(error is None, group):
+                _PEER_WORLDS.add((rank, world))
+                return rank, world
+        if requested == "peer":
+            raise error if error is not None else RuntimeError("another rank could not set up the peer exchange")
+        warnings.warn(f"peer-memory exchange unavailable ({error or 'on another rank'}): using NCCL")
+    elif exchange != "nccl":
         raise ValueError("exchange must be 'peer' or 'nccl'")
     device = model.device if model.device is not None else torch.cuda.current_device()
     # the library keeps one communicator per (device, rank, world) for the life of the process;
@@ -93,6 +118,13 @@ def attach(model, group=None, exchange: Optional[str] = None) -> Tuple[int, int]
     uid = None if world_is_cached(device, rank, world) else broadcast_unique_id(nccl_unique_id, group)
     model.attach_world(rank, world, uid)
     return rank, world
+
+
+def _all_ok(ok: bool, group=None) -> bool:
+    """True when ``ok`` holds on every rank (all-reduce MIN of a flag)."""
+    t = torch.tensor([1 if ok else 0], dtype=torch.int32, device=_host_device(group))
+    dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+    return bool(t.item())
 
 
 def max_over_ranks(value: float, group=None) -> float:

@@ -39,7 +39,7 @@ def _worker(rank, world_size, port, out_dir):
         # 1c. world.attach over the peer exchange: every rank exports, the blobs are all-gathered in
         # rank order and handed to attach_peers; the NCCL exchange broadcasts rank 0's unique id
         class FakeModel:
-            device = None
+            device = 0
 
             def __init__(self):
                 self.calls = []
@@ -58,6 +58,33 @@ def _worker(rank, world_size, port, out_dir):
         assert world.attach(fm, exchange="peer") == (rank, world_size)
         assert fm.calls[0] == ("export", rank, world_size)
         assert fm.calls[1] == ("peers", b"".join(bytes([10 + r]) * 464 for r in range(world_size)), 464)
+        assert (rank, world_size) in world._PEER_WORLDS      # later attaches skip the agreement round
+        world._PEER_WORLDS.clear()
+        # a rank that cannot map peer memory drags every rank to the NCCL exchange, together
+        class NoPeers(FakeModel):
+            def attach_peers(self, blob, per_rank):
+                if rank == 1:
+                    raise RuntimeError("no peer access")
+                super().attach_peers(blob, per_rank)
+
+        import precomputed_atmospheric_scattering_b200.model as model_mod
+        saved = (model_mod.world_is_cached, model_mod.nccl_unique_id)
+        model_mod.world_is_cached = lambda d, r, w: False
+        model_mod.nccl_unique_id = lambda: bytes(range(128))
+        try:
+            import warnings
+            fm = NoPeers()
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                assert world.attach(fm) == (rank, world_size)
+            assert fm.calls[-1] == ("world", rank, world_size, bytes(range(128)))
+            try:
+                world.attach(NoPeers(), exchange="peer")      # asked for explicitly: no silent fallback
+                raise AssertionError("explicit peer exchange fell back")
+            except RuntimeError:
+                pass
+        finally:
+            model_mod.world_is_cached, model_mod.nccl_unique_id = saved
         try:
             world.attach(FakeModel(), exchange="carrier pigeon")
             raise AssertionError("unknown exchange accepted")
