@@ -1,6 +1,6 @@
 """Analytic known-answer tests of the fp64 oracle (oracle/pas_oracle.c).
 
-The reference ships no golden table data; what pins its hot path are the 25 analytic property
+The reference ships no golden table data; what pins its hot path are the 26 analytic property
 checks of atmosphere/reference/functions_test.cc (small synthetic planet, :51-61, tolerance 1e-3
 unless noted). They are restated here against the oracle's point functions: same planet, same
 closed forms, same tolerances. CPU only.
@@ -131,6 +131,49 @@ def test_transmittance_lookup_equals_compute(O):  # :583-632
     assert abs(o.get_transmittance(T, BOTTOM, 0.0, d, False)[0] - want) < EPS
     assert abs(o.get_transmittance(T, r, 0.7, d, False)[0] - want) < EPS
     assert abs(o.get_transmittance(T, r, -0.7, d, o.ray_intersects_ground(r, -0.7))[0] - want) < EPS
+
+
+def _integrand(o, T, r, mu, mu_s, nu, d, hit):
+    """ComputeSingleScatteringIntegrand (functions.glsl:650-668) from the oracle's point functions:
+    T(p -> q) * T_sun(q) * density(q), with q at distance d along the ray."""
+    r_d = min(max(math.sqrt(d * d + 2.0 * r * mu * d + r * r), BOTTOM), TOP)
+    mu_s_d = min(max((r * mu_s + d * nu) / r_d, -1.0), 1.0)
+    t = o.get_transmittance(T, r, mu, d, hit)[0] * o.get_transmittance_to_sun(T, r_d, mu_s_d)[0]
+    return t * o.profile_density(0, r_d - BOTTOM), t * o.profile_density(1, r_d - BOTTOM)
+
+
+def test_single_scattering_integrand(O):  # :676-736
+    o = O()
+    T = o.transmittance()
+    h_top = TOP - BOTTOM
+    h = h_top / 2.0
+    # vertical ray from the ground, sun at the zenith, scattering in the middle of the atmosphere
+    ray, mie = _integrand(o, T, BOTTOM, 1.0, 1.0, 1.0, h, False)
+    tau_r = K_RAYLEIGH * H_RAYLEIGH * (1 - math.exp(-h_top / H_RAYLEIGH))
+    tau_m = K_MIE_EXT * H_MIE * (1 - math.exp(-h_top / H_MIE))
+    assert abs(ray - math.exp(-tau_r - tau_m) * math.exp(-h / H_RAYLEIGH)) < EPS
+    assert abs(mie - math.exp(-tau_r - tau_m) * math.exp(-h / H_MIE)) < EPS
+    # vertical ray looking down from the top boundary, scattering angle 180 degrees
+    ray, mie = _integrand(o, T, TOP, -1.0, 1.0, -1.0, h, True)
+    tau_r = 2 * K_RAYLEIGH * H_RAYLEIGH * (math.exp(-h / H_RAYLEIGH) - math.exp(-h_top / H_RAYLEIGH))
+    tau_m = 2 * K_MIE_EXT * H_MIE * (math.exp(-h / H_MIE) - math.exp(-h_top / H_MIE))
+    assert abs(ray - math.exp(-tau_r - tau_m) * math.exp(-h / H_RAYLEIGH)) < EPS
+    assert abs(mie - math.exp(-tau_r - tau_m) * math.exp(-h / H_MIE)) < EPS
+    # horizontal ray from the ground, sun at the horizon, uniform air without aerosols
+    o = O(uniform_planet(aerosols=False))
+    T = o.transmittance()
+    ray, _ = _integrand(o, T, BOTTOM, 0.0, 0.0, 1.0, 50.0, False)
+    assert abs(ray - math.exp(-K_RAYLEIGH * math.sqrt(TOP * TOP - BOTTOM * BOTTOM))) < EPS
+
+
+def test_distance_to_nearest_boundary(O):  # :745-780; DistanceToNearestAtmosphereBoundary, functions.glsl:680-687
+    o = O()
+    nearest = lambda r, mu: (o.distance_to_bottom(r, mu) if o.ray_intersects_ground(r, mu)
+                             else o.distance_to_top(r, mu))
+    r = BOTTOM * 0.2 + TOP * 0.8
+    assert abs(nearest(r, 1.0) - (TOP - r)) < 1e-3                        # 1 m
+    assert abs(nearest(r, 0.0) - math.sqrt(TOP * TOP - r * r)) < 1e-3
+    assert abs(nearest(r, -1.0) - (r - BOTTOM)) < 1e-3
 
 
 def test_single_scattering_analytic(O):  # :818-858
