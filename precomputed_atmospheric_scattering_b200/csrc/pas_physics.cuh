@@ -1,5 +1,5 @@
-// Host/device inline physics shared by every kernel of the engine (and by the host-compiled
-// numerics emulation in tests/emu/, which includes this header with a plain C++ compiler).
+// Host/device inline physics shared by every kernel of the engine and by the host code of
+// pas_model.cu (the header also compiles with a plain C++ compiler).
 //
 // Two tiers:
 //   * fp64 "setup" math: texel -> (r, mu, mu_s, nu) inverse mappings and the per-(layer,
