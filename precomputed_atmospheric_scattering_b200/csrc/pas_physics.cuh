@@ -1,5 +1,6 @@
 // Host/device inline physics shared by every kernel of the engine and by the host code of
-// pas_model.cu (the header also compiles with a plain C++ compiler).
+// pas_model.cu. The header also compiles with a plain C++ compiler: tests/emu/physics_host.cc
+// exports it to tests/test_physics_header.py, which checks every mapping against the oracle on the CPU.
 //
 // Two tiers:
 //   * fp64 "setup" math: texel -> (r, mu, mu_s, nu) inverse mappings and the per-(layer,
