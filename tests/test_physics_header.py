@@ -143,3 +143,41 @@ def test_interpolation_taps_follow_the_reference_rule(emu):
                 v = lambda k: 10.0 + 3.0 * k
                 got = v(i0.value) * (1 - w.value) + v(i1.value) * w.value
                 assert got == pytest.approx(v(x), abs=1e-5)
+
+
+def test_unclamped_texels_sit_exactly_on_a_nu_slab(emu, orc):
+    """multiple_scattering_rows_kernel takes a 2-texel path for texels whose nu lies exactly on a slab
+    of the source table: at the reference's sizes that is every texel whose nu
+    was not clamped by functions.glsl:923-925 -- about 70 % -- because the slab value survives the
+    round trip nu -> texel coordinate with a tap weight of exactly 0 or 1 in fp32."""
+    sizes = dict(t_w=256, t_h=64, r=32, mu=128, mu_s=32, nu=8, e_w=64, e_h=16)
+    spec = pas.earth(3, max_sun_zenith_deg=102.0)
+    cp = pas.channel_params(spec, [680.0, 550.0, 440.0])
+    o = orc.Oracle(cp, orc.Sizes(**sizes))
+    g = _Geometry()
+    for a, b in (("t_w", "t_w"), ("t_h", "t_h"), ("r_n", "r"), ("mu_n", "mu"), ("mu_s_n", "mu_s"), ("nu_n", "nu"),
+                 ("e_w", "e_w"), ("e_h", "e_h")):
+        setattr(g.sz, a, sizes[b])
+    g.bottom, g.top = cp.bottom_radius, cp.top_radius
+    g.H = math.sqrt(g.top * g.top - g.bottom * g.bottom)
+    g.mu_s_min = cp.mu_s_min
+    g.mus_A = (o.distance_to_top(g.bottom, g.mu_s_min) - (g.top - g.bottom)) / (g.H - (g.top - g.bottom))
+    out = (ctypes.c_double * 5)()
+    i0, i1, w = ctypes.c_int(), ctypes.c_int(), ctypes.c_float()
+    on_slab = unclamped = total = 0
+    for k in range(0, 32, 5):
+        for j in range(0, 128, 7):
+            for i_mu_s in range(32):
+                for i_nu in range(8):
+                    emu.emu_texel(ctypes.byref(g), k, j, i_mu_s, i_nu, out)
+                    nu = out[3]
+                    emu.emu_make_tap((nu + 1.0) * 0.5 * 7, 8, ctypes.byref(i0), ctypes.byref(i1), ctypes.byref(w))
+                    slab = w.value == 0.0 or w.value == 1.0 or i0.value == i1.value
+                    knot = i_nu / 7.0 * 2.0 - 1.0
+                    total += 1
+                    on_slab += slab
+                    if nu == max(-1.0, min(1.0, knot)):          # not clamped by (mu, mu_s)
+                        unclamped += 1
+                        assert slab, (k, j, i_mu_s, i_nu, nu, w.value)
+                        assert (i1.value if w.value == 1.0 else i0.value) == i_nu
+    assert 0.6 < unclamped / total < 0.8 and on_slab >= unclamped
