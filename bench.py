@@ -234,7 +234,11 @@ def run_b200(args, rank, world_size, local_rank):
     distributed = world_size > 1
     if distributed:
         import torch.distributed as dist
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout to the one JSON line
+        # keep stdout to the one JSON line: NCCL prints "NCCL version ..." on stdout at the VERSION
+        # level and honours NCCL_DEBUG_FILE only above it
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     def barrier():
