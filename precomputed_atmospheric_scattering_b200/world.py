@@ -136,3 +136,12 @@ def max_over_ranks(value: float, group=None) -> float:
     t = torch.tensor([float(value)], dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
     return float(t.item())
+
+
+def sum_over_ranks(value: float, group=None) -> float:
+    """Sum of ``value`` over the ranks (used by the bench to count the ranks whose parity check failed)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return float(value)
+    t = torch.tensor([float(value)], dtype=torch.float64, device=_host_device(group))
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return float(t.item())

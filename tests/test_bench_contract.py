@@ -56,3 +56,52 @@ def test_ncu_evidence_file_names_the_kernels_the_bench_times():
         e = ncu["passes"][key]
         assert key in flops and e["traffic_bytes"] > 0 and 0 < e["fma_pipe_cycles_active_pct"] <= 100
         assert "kernel" in e and e["launches_averaged"] >= 1
+
+
+def test_ncu_census_gives_executed_fractions_below_one():
+    """roofline.frac = executed fp32 flops (SASS opcode census of the ncu capture) / time / FMA peak:
+    with the capture's own durations and the nominal 74.5 TFLOP/s no pass reaches the peak, and the
+    ray marches report their real bound, the L1 data pipe (wavefronts per SM / elapsed cycles)."""
+    ncu = json.load(open(os.path.join(ROOT, "profiles", "ncu_hot_kernels.json")))
+    for key, e in ncu["passes"].items():
+        ops = e["thread_instructions"]
+        flop = (2 * ops.get("FFMA", 0) + 4 * ops.get("FFMA2", 0) + ops.get("FMUL", 0) + 2 * ops.get("FMUL2", 0) +
+                ops.get("FADD", 0) + 2 * ops.get("FADD2", 0))
+        assert flop == pytest.approx(e["fp32_flop_executed"], rel=1e-6)
+        frac = e["fp32_flop_executed"] / (e["ms_under_ncu"] * 1e-3) / 74.5e12
+        assert 0.05 < frac < 1.0, (key, frac)
+        # the executed fraction cannot exceed what the FMA pipe was busy
+        assert frac <= e["fma_pipe_cycles_active_pct"] / 100 + 0.02, (key, frac)
+        wf = e["l1_wavefronts_per_sm"] / e["sm_cycles_elapsed"]
+        assert wf == pytest.approx(e["l1_data_pipe_wavefronts_pct"] / 100, abs=0.02), key
+    assert "FFMA2" in ncu["passes"]["scattering_density_n"]["thread_instructions"]   # Blackwell packed fp32
+
+
+def test_both_arms_print_the_same_config_object():
+    for cfg in bench.CONFIGS:
+        for n in (1, 2, 8):
+            a, b = bench.config_dict(cfg, n), bench.config_dict(cfg, n)
+            assert a == b and a["baseline_config"] == cfg and a["workload"] == bench.CONFIGS[cfg]["workload"]
+            assert "l2" in a and ("1 GPU" if n == 1 else f"{n} GPUs") in a["parallelism"]
+    assert bench.CONFIGS[2]["metric"] == "lut_precompute_ms_4_orders_15_wavelengths"
+    # the driver's default line is config 2
+    import argparse  # noqa: F401
+    assert bench.CONFIGS[2]["wavelengths"] == 15 and bench.CONFIGS[2]["orders"] == 4
+
+
+def test_parity_check_flags_a_wrong_table():
+    """bench.py's `parity` key: the check passes on the reference's own numbers pushed through the
+    product format and fails when one row of S is scaled by 1 %."""
+    import numpy as np
+    from tests import parity
+    two, _, _ = parity.load_golden()
+    rows = parity.load_rows()
+    # RGB mode (config 1): a table whose rows reproduce the digests cannot be built without the full
+    # reference tables, so exercise the failure path: zeros are out of tolerance everywhere
+    S = np.zeros((32, 128, 256, 4), dtype=np.float32)
+    E = np.moveaxis(two["irradiance"][15:18], 0, -1).astype(np.float32)
+    T = np.moveaxis(two["transmittance"][15:18], 0, -1).astype(np.float32)
+    m = bench.parity_check(1, S, np.concatenate([E, np.ones_like(E[..., :1])], -1),
+                           np.concatenate([T, np.ones_like(T[..., :1])], -1), None, False)
+    assert not m["ok"] and m["irradiance"] < 1e-6 and m["transmittance"] < 1e-6 and m["scattering_row_sums"] > 0.5
+    assert m["n_texels"] == 32 * 128 * 256 * 4 + 3 * 16 * 64 + 3 * 64 * 256

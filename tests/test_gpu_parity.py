@@ -78,6 +78,44 @@ def test_earth_intermediates_match_reference_golden(which, earth_rgb, earth_spec
     print(f"{which}: worst floored relative error over all tables {worst:.3e}")
 
 
+@pytest.mark.parametrize("which", ["rgb", "spectral"])
+def test_every_row_of_every_table_matches_the_reference_digest(which, earth_rgb, earth_spectral):
+    """All 1,048,576 texels of every 3-D intermediate (not only the 3,240 sampled ones): sum, weighted
+    sum and max of each of the 4096 rows of 256 texels against the digests of the reference run
+    (tests/golden/earth18_rows.npz, oracle/gen_row_digest.py)."""
+    rows = parity.load_rows()
+    spec, model = earth_rgb if which == "rgb" else earth_spectral
+    lanes = slice(15, 18) if which == "rgb" else slice(0, 15)
+    worst = {}
+    for name in NAMES_3D:
+        m = parity.digest_metrics(model.intermediate(name), rows, name, lanes)
+        assert m["nan"] == 0 and m["worst"] <= TIGHT, (name, m)
+        worst[name] = m["worst"]
+    if which == "rgb":
+        # radiance mode: the product table is the per-channel sum of the reference (identity matrix)
+        S = np.moveaxis(model.scattering[..., :3], -1, 0)
+        m = parity.digest_metrics(S, rows, "scattering", lanes)
+        assert m["worst"] <= TIGHT, m
+        worst["scattering"] = m["worst"]
+    print(f"{which}: worst row-digest error {max(worst.values()):.3e} over {len(worst)} tables x 4096 rows")
+
+
+def test_bench_product_fp16_combined_luminance(pas, golden):
+    """The product bench.py times (BASELINE config 2 with the demo's settings: 15 wavelengths,
+    combined textures, HALF-precision final tables), against the reference: every row of S (fp16 RGBA)
+    against the digests of the luminance table computed from the reference's fp64 tables, E and T
+    against the golden 2-D tables. bench.py prints the same check as its `parity` key at every N."""
+    two, _, _ = golden
+    model = pas.Model.from_spec(pas.earth(15, half_precision=True, combine_scattering_textures=True))
+    model.Init(4)
+    assert model.texture_info(pas.TEXTURE_SCATTERING).bytes_per_channel == 2
+    m = parity.check_bench_product(model.scattering, model.irradiance, model.transmittance,
+                                   model.luminance_matrix(), two, parity.load_rows(), half_precision=True)
+    assert m["ok"], m
+    print("bench product parity:", m)
+    model.close()
+
+
 def test_earth_rgb_final_tables(earth_rgb, golden):
     two, three, _ = golden
     _, model = earth_rgb
