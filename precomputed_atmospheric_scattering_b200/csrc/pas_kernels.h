@@ -33,8 +33,8 @@ struct PeerTables {
 };
 
 // The scattering layers a launch works on: begin, begin + stride, ... < end. One GPU: all of them.
-// Several GPUs: a contiguous slab per rank (NCCL exchange) or every world-th layer (peer exchange:
-// the cost of a layer grows with its altitude, interleaving balances the ranks).
+// Several GPUs: a contiguous slab per rank, with either exchange (dealing every world-th layer to a
+// rank was measured slower; the kernels accept any stride).
 struct LayerSet {
   int begin, end, stride;
   int count() const { return end > begin ? (end - begin + stride - 1) / stride : 0; }
@@ -107,17 +107,28 @@ cudaError_t launch_multiple_scattering(const PasGeometry& g, const PasSpectrum& 
                                        cudaStream_t stream);
 
 // ---- multi-GPU exchange over peer memory (peer_exchange.cu) ---------------------------------------
-struct PeerFlags {                 // flags[r]: the flag array of rank r (own memory or IPC mapping)
+// Flag array of a rank: PAS_FLAG_CHANNELS independent barrier sequences ("channels": main stream, side
+// stream) of PAS_FLAG_WORDS words each. Word p < 8 of a channel: the last epoch rank p has signalled
+// (written by rank p); word PAS_FLAG_EPOCH: the rank's own epoch counter of the channel, advanced by
+// its barrier kernels themselves (no host-side epoch: the same enqueued sequence can be replayed);
+// word PAS_FLAG_POISON of channel 0: set by any rank whose barrier timed out -- every later barrier of
+// every rank then fails at once instead of running on with stale data.
+#define PAS_FLAG_CHANNELS 2
+#define PAS_FLAG_WORDS 16
+#define PAS_FLAG_EPOCH 8
+#define PAS_FLAG_POISON 15
+struct PeerFlags {                 // flags[r]: the channel's words in the flag array of rank r
   int rank, world;
   unsigned* flags[PAS_MAX_PEERS + 1];
-  int* error;                      // mapped host memory, set when a barrier times out
+  unsigned* poison[PAS_MAX_PEERS + 1];   // the poison word of rank r
+  int* error;                      // mapped host memory: 1 = this rank timed out, 2 = poisoned by a peer
 };
 struct PeerTargets {               // destinations of a push: the same buffer on every rank
   int n;
   void* dst[PAS_MAX_PEERS + 1];
 };
-// Cross-GPU barrier number `epoch` (epochs increase by one per barrier, in step on every rank).
-cudaError_t launch_peer_barrier(const PeerFlags& f, unsigned epoch, cudaStream_t stream);
+// Next cross-GPU barrier of the channel (epochs advance by one per barrier, in step on every rank).
+cudaError_t launch_peer_barrier(const PeerFlags& f, cudaStream_t stream);
 // Copies `chunks` byte ranges [offset + i * stride, offset + i * stride + bytes) of src to the same
 // ranges of every target.
 cudaError_t launch_peer_push(const void* src, size_t bytes, size_t offset_bytes, const PeerTargets& t,

@@ -260,16 +260,19 @@ CommCache& comm_cache() {
 }
 
 // Peer-memory worlds: per (device, rank, world size) one flag array (the other ranks signal their
-// barrier epochs into it), the epoch counter and the error word of the barrier kernel; plus the
-// IPC mappings already opened by this process (buffers come back from the pool with the same
+// barrier epochs into it; the epoch counters of the two barrier channels live beside the flags and
+// are advanced by the barrier kernels, pas_kernels.h) and the error word of the barrier kernel; plus
+// the IPC mappings already opened by this process (buffers come back from the pool with the same
 // handles, so re-created models find their peers' tables mapped).
-constexpr int kBarrierChannels = 2;   // main stream, side stream: independent barrier sequences
-constexpr int kChannelWords = 16;
+// The flag array is ONE barrier sequence per channel for the whole process: two models of the same
+// world in flight at once would draw interleaved epochs and release each other's barriers early, so
+// pas_model_init_async admits one model per PeerWorld at a time (`in_flight`).
 struct PeerWorld {
-  unsigned* flags = nullptr;   // device memory, kBarrierChannels x kChannelWords words, zero at creation
+  unsigned* flags = nullptr;   // device memory, PAS_FLAG_CHANNELS x PAS_FLAG_WORDS words, zero at creation
   int* error_host = nullptr;   // pinned, mapped
   int* error_dev = nullptr;
-  unsigned epoch[kBarrierChannels] = {0, 0};
+  const pas_model* in_flight = nullptr;  // the model whose Init is enqueued and not yet waited for
+  bool broken = false;         // a barrier timed out: epochs and tables of the ranks are out of step
 };
 struct PeerCache {
   std::mutex mu;
@@ -334,6 +337,7 @@ struct pas_model {
   int launches = 0;
   // ---- multi-GPU ----
   int rank = 0, world = 1;
+  int pending_rank = 0, pending_world = 0;  // of pas_model_ipc_export, until pas_model_attach_peers succeeds
   ncclComm_t comm = nullptr;
   // peer-memory exchange (pas_model_attach_peers): tables of the other ranks, indexed by rank
   bool peer = false;
@@ -600,9 +604,12 @@ pas_status peer_barrier(pas_model* m, int channel, cudaStream_t stream) {
   pas::PeerFlags f{};
   f.rank = m->rank;
   f.world = m->world;
-  for (int r = 0; r < m->world; ++r) f.flags[r] = m->peer_flags[r] + channel * kChannelWords;
+  for (int r = 0; r < m->world; ++r) {
+    f.flags[r] = m->peer_flags[r] + channel * PAS_FLAG_WORDS;
+    f.poison[r] = m->peer_flags[r] + PAS_FLAG_POISON;
+  }
   f.error = m->pw->error_dev;
-  PAS_CUDA(pas::launch_peer_barrier(f, ++m->pw->epoch[channel], stream));
+  PAS_CUDA(pas::launch_peer_barrier(f, stream));
   m->launches += 1;
   return PAS_OK;
 }
@@ -629,6 +636,13 @@ pas_status run_phase(pas_model* m, int gi, int phase, int order, bool accumulate
         const int base = g.sz.t_h / m->world, extra = g.sz.t_h % m->world;
         const int j0 = m->rank * base + std::min(m->rank, extra);
         const int j1 = j0 + base + (m->rank < extra ? 1 : 0);
+        if (gi > 0) {
+          // the rows go straight into the other ranks' T, which their ray marches of the previous
+          // channel group may still be reading (the last barrier of a group comes before its last
+          // multiple-scattering pass, and Init(1) has none after phase 0): all ranks meet first
+          pas_status st = peer_barrier(m, channel, stream);
+          if (st != PAS_OK) return st;
+        }
         PAS_CUDA(pas::launch_transmittance_rows(g, sp, m->T.f(), mirrors, j0, j1, stream));
         pas_status st = peer_barrier(m, channel, stream);
         if (st != PAS_OK) return st;
@@ -887,6 +901,11 @@ void pas_model_destroy(pas_model* m) {
     cudaStreamSynchronize(m->stream);
     if (m->aux) cudaStreamSynchronize(m->aux);
     if (m->copy) cudaStreamSynchronize(m->copy);
+    if (m->pw != nullptr) {
+      PeerCache& cache = peer_cache();
+      std::lock_guard<std::mutex> lock(cache.mu);
+      if (m->pw->in_flight == m) m->pw->in_flight = nullptr;
+    }
     StreamSet ss;
     ss.copy = m->copy;
     ss.ev_copy = m->ev_copy;
@@ -925,9 +944,20 @@ pas_status pas_model_wait(pas_model* m) {
   m->in_flight = false;
   PAS_CUDA(cudaStreamSynchronize(m->stream));
   PhaseTimer(nullptr_model_tag(), m).finish();
-  if (m->peer && *m->pw->error_host != 0) {
-    *m->pw->error_host = 0;
-    return fail(PAS_ERR_NCCL, "peer barrier timed out: another rank failed or is out of step");
+  if (m->peer) {
+    PeerCache& cache = peer_cache();
+    std::lock_guard<std::mutex> lock(cache.mu);
+    if (m->pw->in_flight == m) m->pw->in_flight = nullptr;
+    const int code = *m->pw->error_host;
+    if (code != 0) {
+      // the barrier epochs and the tables of the ranks are out of step from here on: the peer world
+      // of this (device, rank, world) stays unusable (attach the models to an NCCL world instead)
+      *m->pw->error_host = 0;
+      m->pw->broken = true;
+      return fail(PAS_ERR_NCCL, code == 1 ? "peer barrier timed out: another rank failed or is out of step "
+                                            "(PAS_PEER_TIMEOUT_MS sets the wait)"
+                                          : "another rank's peer barrier timed out: this Init used stale tables");
+    }
   }
   m->initialised = true;
   return PAS_OK;
@@ -940,6 +970,18 @@ pas_status pas_model_init_async(pas_model* m, unsigned int num_scattering_orders
   if (m->in_flight) {
     pas_status st = pas_model_wait(m);
     if (st != PAS_OK) return st;
+  }
+  if (m->peer) {
+    PeerCache& cache = peer_cache();
+    std::lock_guard<std::mutex> lock(cache.mu);
+    if (m->pw->broken) {
+      return fail(PAS_ERR_NCCL, "the peer world of this rank is out of step after a barrier timeout");
+    }
+    if (m->pw->in_flight != nullptr && m->pw->in_flight != m) {
+      return fail(PAS_ERR_STATE, "another model of this peer world has an Init in flight: wait for it first "
+                                 "(the ranks share one barrier sequence per world)");
+    }
+    m->pw->in_flight = m;
   }
   m->launches = 0;
   // Overlapped schedule (single GPU, no captures): the irradiance pass of order n depends on the
@@ -1037,6 +1079,10 @@ pas_status pas_model_init_async(pas_model* m, unsigned int num_scattering_orders
       PAS_CUDA(side_after_main());
       if ((st = run_phase(m, (int)gi, 4, (int)order - 1, blend, side, ds_in, ds_out, overlap ? 1 : 0)) != PAS_OK) return st;
       if (!overlap) timer.mark("indirect_irradiance_" + tag);
+      // peer worlds: phase 4 has enqueued the barrier that completes the density slabs on the main
+      // stream; what a rank waits there (the slowest rank's density pass + the drain of its stores)
+      // is timed apart from the multiple-scattering kernel that follows
+      if (overlap && m->peer) timer.mark("exchange_wait_" + tag);
       if ((st = capture_copy(m, "delta_irradiance_" + tag, m->dE.f(), m->n_e(), nc, off, false)) != PAS_OK) return st;
       // (multi-GPU: the density table is complete once the exchange of phase 3 / 4 is done)
       if ((st = capture_copy(m, "delta_density_" + tag, m->cur_dJ(), m->n_s(), nc, off, true)) != PAS_OK) return st;
@@ -1416,8 +1462,9 @@ pas_status pas_model_ipc_export(pas_model* m, int rank, int world_size, void* ou
     return fail(PAS_ERR_UNSUPPORTED, "scattering_r must be divisible by the world size");
   }
   PAS_CUDA(cudaSetDevice(m->device));
-  m->rank = rank;
-  m->world = world_size;
+  // rank and world take effect in pas_model_attach_peers, once every mapping has succeeded
+  m->pending_rank = rank;
+  m->pending_world = world_size;
   const size_t cp = PAS_CHANNEL_PITCH(m->max_nc());
   PAS_CUDA(m->dJ2.ensure(m->n_s() * cp * sizeof(float)));
   PAS_CUDA(m->xE.ensure((size_t)2 * world_size * m->xe_stride() * sizeof(float)));
@@ -1433,7 +1480,6 @@ pas_status pas_model_ipc_export(pas_model* m, int rank, int world_size, void* ou
       *w.error_host = 0;
       PAS_CUDA(cudaHostGetDevicePointer(&w.error_dev, w.error_host, 0));
       PAS_CUDA(cudaDeviceSynchronize());
-      w.epoch[0] = w.epoch[1] = 0;
     }
     m->pw = &w;
   }
@@ -1469,15 +1515,17 @@ pas_status open_peer(const cudaIpcMemHandle_t& h, void** ptr) {
 
 pas_status pas_model_attach_peers(pas_model* m, const void* exports, size_t bytes_per_rank) {
   if (m == nullptr || exports == nullptr) return fail(PAS_ERR_INVALID_ARGUMENT, "NULL argument");
-  if (m->pw == nullptr || m->world < 2) {
+  if (m->pw == nullptr || m->pending_world < 2) {
     return fail(PAS_ERR_INVALID_ARGUMENT, "call pas_model_ipc_export first");
   }
   if (bytes_per_rank != sizeof(PasIpcExport)) return fail(PAS_ERR_INVALID_ARGUMENT, "bad export size");
   PAS_CUDA(cudaSetDevice(m->device));
-  for (int r = 0; r < m->world; ++r) {
+  const int rank = m->pending_rank, world = m->pending_world;
+  m->peer = false;  // until every peer is mapped
+  for (int r = 0; r < world; ++r) {
     PasIpcExport e;
     std::memcpy(&e, static_cast<const char*>(exports) + (size_t)r * bytes_per_rank, sizeof e);
-    if (r == m->rank) {
+    if (r == rank) {
       m->peer_T[r] = m->T.f();
       m->peer_dJ[0][r] = m->dJ.f();
       m->peer_dJ[1][r] = m->dJ2.f();
@@ -1507,6 +1555,8 @@ pas_status pas_model_attach_peers(pas_model* m, const void* exports, size_t byte
     if ((st = open_peer(e.flags, &p)) != PAS_OK) return st;
     m->peer_flags[r] = static_cast<unsigned*>(p);
   }
+  m->rank = rank;
+  m->world = world;
   m->peer = true;
   m->exchanges = 0;
   return PAS_OK;

@@ -8,9 +8,12 @@
 //   * peer_barrier: every rank writes the epoch number into its slot of every other rank's flag
 //     array (release, system scope) and waits until all the slots of its own array have reached it.
 //     Stream order + the fence make the stores of the kernels enqueued before the barrier visible
-//     to the kernels every rank enqueues after it.
+//     to the kernels every rank enqueues after it. A rank that waits longer than the timeout fails
+//     its Init and poisons the flag arrays of all ranks, so that every rank fails the same Init.
 //   * sum_partials: irradiance = sum over ranks of the partial sums, in rank order on every rank
 //     (bit-identical results everywhere).
+#include <cstdlib>
+
 #include "pas_kernels.h"
 
 namespace pas {
@@ -22,20 +25,41 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
   return t;
 }
 
-__global__ void peer_barrier_kernel(PeerFlags f, unsigned epoch, unsigned long long timeout_ns) {
+__global__ void peer_barrier_kernel(PeerFlags f, unsigned long long timeout_ns) {
   const int p = threadIdx.x;
+  // the channel's epoch counter lives beside the flags and is advanced here, by the one warp of the
+  // one barrier kernel that can run at a time on the channel's stream
+  unsigned epoch = 0;
+  if (p == 0) {
+    unsigned* counter = f.flags[f.rank] + PAS_FLAG_EPOCH;
+    epoch = *counter + 1;
+    *counter = epoch;
+  }
+  epoch = __shfl_sync(0xffffffffu, epoch, 0);
   if (p >= f.world || p == f.rank) return;
   __threadfence_system();
   unsigned* dst = f.flags[p] + f.rank;
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(dst), "r"(epoch) : "memory");
   const unsigned* src = f.flags[f.rank] + p;
+  const unsigned* poison = f.poison[f.rank];
   const unsigned long long t0 = global_timer_ns();
   for (;;) {
-    unsigned v;
+    unsigned v, bad;
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(src) : "memory");
+    asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(bad) : "l"(poison) : "memory");
+    if (bad != 0) {
+      // another rank gave up waiting: its tables and ours are out of step; fail this Init too
+      *f.error = 2;
+      break;
+    }
     if ((int)(v - epoch) >= 0) break;
     if (global_timer_ns() - t0 > timeout_ns) {
-      *f.error = 1;  // mapped host memory: a rank died or fell out of step; Init reports it
+      // a rank died or fell out of step: report it (mapped host memory) and tell every rank, so that
+      // a late rank does not sail through barriers whose flags it finds already set
+      *f.error = 1;
+      for (int r = 0; r < f.world; ++r) {
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f.poison[r]), "r"(1u) : "memory");
+      }
       break;
     }
     __nanosleep(200);
@@ -66,8 +90,15 @@ __global__ void sum_partials_kernel(const float* __restrict__ parts, int world, 
 
 }  // namespace
 
-cudaError_t launch_peer_barrier(const PeerFlags& f, unsigned epoch, cudaStream_t stream) {
-  peer_barrier_kernel<<<1, 32, 0, stream>>>(f, epoch, 5000000000ull);
+cudaError_t launch_peer_barrier(const PeerFlags& f, cudaStream_t stream) {
+  // PAS_PEER_TIMEOUT_MS: how long a rank waits for the others before it fails the Init (default 5 s;
+  // raise it when ranks may start their Init calls further apart than that)
+  static const unsigned long long timeout_ns = [] {
+    const char* e = getenv("PAS_PEER_TIMEOUT_MS");
+    const long long ms = e != nullptr ? atoll(e) : 0;
+    return (unsigned long long)(ms > 0 ? ms : 5000) * 1000000ull;
+  }();
+  peer_barrier_kernel<<<1, 32, 0, stream>>>(f, timeout_ns);
   return cudaGetLastError();
 }
 

@@ -89,10 +89,25 @@ def attach(model, group=None, exchange: Optional[str] = None) -> Tuple[int, int]
         # memory (no P2P between the devices, IPC disabled in the container) tells the others, and
         # unless the peer exchange was asked for explicitly all of them fall back to NCCL together.
         if (rank, world) in _PEER_WORLDS:
-            # this process has already mapped its peers once (and so has every other rank): no need
-            # to agree again; a failure now is an error, not a reason to change the exchange
-            blob = model.ipc_export(rank, world)
-            model.attach_peers(all_gather_bytes(blob, group), len(blob))
+            # this process has already mapped its peers once (and so has every other rank): the
+            # exchange is settled, a failure now is an error. The one collective still carries a
+            # status byte per rank, so that a rank whose export failed (out of memory while growing
+            # its buffers) takes every rank out together instead of leaving them in the all-gather.
+            from .model import IPC_EXPORT_BYTES
+            blob, error = bytes(IPC_EXPORT_BYTES), None
+            try:
+                blob = model.ipc_export(rank, world)
+            except Exception as e:  # PasError
+                error = e
+            packed = all_gather_bytes(bytes([0 if error else 1]) + blob, group)
+            n = 1 + len(blob)
+            ok = [packed[r * n] == 1 for r in range(world)]
+            if not all(ok):
+                raise error if error is not None else RuntimeError(
+                    f"rank {ok.index(False)} could not export its peer tables")
+            # (a rank failing to MAP a peer here raises alone; the others fail their next Init at the
+            # first flag barrier, which times out and poisons every rank's flags: no silent corruption)
+            model.attach_peers(b"".join(packed[r * n + 1:(r + 1) * n] for r in range(world)), len(blob))
             return rank, world
         blob, error = b"", None
         try:

@@ -84,8 +84,8 @@ def _variant_worker(rank, world_size, port, out_dir):
     dist.init_process_group("nccl", rank=rank, world_size=world_size,
                             device_id=torch.device("cuda", rank))
     try:
-        for name, spec, orders in _variants(pas):
-            model = pas.Model.from_spec(spec, device=rank, sizes=SIZES)
+        for name, spec, orders, sizes in _variants(pas):
+            model = pas.Model.from_spec(spec, device=rank, **sizes)
             world.attach(model, exchange="peer")
             model.Init(orders)
             out = dict(S=model.scattering, E=model.irradiance, T=model.transmittance)
@@ -93,6 +93,24 @@ def _variant_worker(rank, world_size, port, out_dir):
                 out["M"] = model.single_mie_scattering
             np.savez(os.path.join(out_dir, f"{name}_rank{rank}.npz"), **out)
             model.close()
+        # one barrier sequence per peer world: a second model of the world cannot start its Init while
+        # the first is in flight (its barriers would release the first model's early); once the first
+        # has been waited for, it runs and gives the same tables
+        a = pas.Model.from_spec(pas.small_planet(), device=rank, sizes=SIZES)
+        b = pas.Model.from_spec(pas.small_planet(), device=rank, sizes=SIZES)
+        world.attach(a, exchange="peer")
+        world.attach(b, exchange="peer")
+        a.InitAsync(3)
+        try:
+            b.InitAsync(3)
+            raise AssertionError("two models of one peer world were in flight")
+        except pas.PasError as e:
+            assert e.status == 5, e     # PAS_ERR_STATE
+        a.Wait()
+        b.Init(3)
+        assert np.array_equal(a.scattering, b.scattering) and np.array_equal(a.irradiance, b.irradiance)
+        a.close()
+        b.close()
         dist.barrier()
     finally:
         dist.destroy_process_group()
@@ -101,12 +119,19 @@ def _variant_worker(rank, world_size, port, out_dir):
 def _variants(pas):
     """Paths of the peer exchange the Earth runs above do not take: a separate single-Mie table with
     fp16 products (second final push), 24 channels = two launch groups (the buffer parity carries
-    over from one group to the next), and Init(1) (no order loop: only the final exchange)."""
+    over from one group to the next; at the reference's full sizes too, where a rank that finishes a
+    group early would otherwise overwrite the transmittance rows its peer still ray-marches with),
+    and Init(1) (no order loop: only the final exchange), also with two groups (no barrier at all
+    between the groups but the one in front of the transmittance rows)."""
     sep = pas.small_planet()
     sep.combine_scattering_textures, sep.half_precision = False, True
     wide = pas.small_planet()
     wide.num_precomputed_wavelengths = 24
-    return [("separate_mie_fp16", sep, 3), ("two_groups", wide, 3), ("single_order", pas.small_planet(), 1)]
+    small = dict(sizes=SIZES)
+    return [("separate_mie_fp16", sep, 3, small), ("two_groups", wide, 3, small),
+            ("single_order", pas.small_planet(), 1, small),
+            ("two_groups_full_size", pas.earth(24, half_precision=False), 2, {}),
+            ("two_groups_full_size_single_order", pas.earth(24, half_precision=False), 1, {})]
 
 
 @pytest.mark.timeout(600)
@@ -115,8 +140,8 @@ def test_peer_exchange_variants(tmp_path, pas):
         pytest.skip("needs >= 2 GPUs")
     import torch.multiprocessing as mp
     mp.spawn(_variant_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
-    for name, spec, orders in _variants(pas):
-        single = pas.Model.from_spec(spec, device=0, sizes=SIZES)
+    for name, spec, orders, sizes in _variants(pas):
+        single = pas.Model.from_spec(spec, device=0, **sizes)
         single.Init(orders)
         want = dict(S=single.scattering, E=single.irradiance, T=single.transmittance)
         if not spec.combine_scattering_textures:

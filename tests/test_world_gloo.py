@@ -59,6 +59,25 @@ def _worker(rank, world_size, port, out_dir):
         assert fm.calls[0] == ("export", rank, world_size)
         assert fm.calls[1] == ("peers", b"".join(bytes([10 + r]) * 464 for r in range(world_size)), 464)
         assert (rank, world_size) in world._PEER_WORLDS      # later attaches skip the agreement round
+        # ... and exchange the blobs with one collective, whose status byte takes every rank out
+        # together when one rank's export fails (instead of leaving the others in the all-gather)
+        fm = FakeModel()
+        assert world.attach(fm, exchange="peer") == (rank, world_size)
+        assert fm.calls[1] == ("peers", b"".join(bytes([10 + r]) * 464 for r in range(world_size)), 464)
+
+        class ExportFails(FakeModel):
+            def ipc_export(self, r, w):
+                if r == 1:
+                    raise MemoryError("out of memory growing the peer buffers")
+                return super().ipc_export(r, w)
+
+        fm = ExportFails()
+        try:
+            world.attach(fm, exchange="peer")
+            raise AssertionError("a failed export went unnoticed")
+        except (MemoryError, RuntimeError) as e:
+            assert isinstance(e, MemoryError) == (rank == 1)
+        assert not any(c[0] == "peers" for c in fm.calls)
         world._PEER_WORLDS.clear()
         # a rank that cannot map peer memory drags every rank to the NCCL exchange, together
         class NoPeers(FakeModel):
