@@ -255,8 +255,9 @@ pas_status pas_model_read_intermediate(pas_model* model, const char* name, float
  * "delta_irradiance" / "delta_density" / "delta_multiple" for the live buffers) and run one phase
  * of atmosphere/model.cc:1048-1215. phase: 0 transmittance, 1 direct irradiance, 2 single
  * scattering, 3 scattering density(order), 4 indirect irradiance(order = order of the radiance
- * integrated), 5 multiple scattering. Results are read back with pas_model_read_intermediate
- * using the live-buffer names. */
+ * integrated), 5 multiple scattering, 6 the per-(layer, direction) ground-transmittance tables of
+ * the density pass alone, from the transmittance buffer as it stands (phase 0 computes both).
+ * Results are read back with pas_model_read_intermediate using the live-buffer names. */
 pas_status pas_model_write_intermediate(pas_model* model, const char* name, const float* src,
                                         size_t num_floats);
 pas_status pas_model_run_phase(pas_model* model, int phase, int order);

@@ -742,6 +742,13 @@ pas_status run_phase(pas_model* m, int gi, int phase, int order, bool accumulate
       m->launches += 1;
       if (m->peer) m->exchanges += 1;  // the next order uses the other density buffer / xE half
       break;
+    case 6:
+      // test hook: the per-(layer, direction) tables of the density pass alone, from whatever the
+      // transmittance buffer holds (device-side known-answer tests write their own transmittance)
+      PAS_CUDA(pas::launch_density_setup(g, sp, m->T.f(), static_cast<PasDensityDir*>(m->dirs.p),
+                                         m->G.f(), m->cR.f(), m->cM.f(), stream));
+      m->launches += 1;
+      break;
     default:
       return fail(PAS_ERR_INVALID_ARGUMENT, "unknown phase");
   }

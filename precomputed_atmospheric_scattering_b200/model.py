@@ -20,7 +20,8 @@ LIB_PATH = os.environ.get("PAS_B200_LIB") or os.path.join(_HERE, "libpas_b200.so
 
 TEXTURE_TRANSMITTANCE, TEXTURE_SCATTERING, TEXTURE_IRRADIANCE, TEXTURE_SINGLE_MIE = 0, 1, 2, 3
 PHASES = {"transmittance": 0, "direct_irradiance": 1, "single_scattering": 2,
-          "scattering_density": 3, "indirect_irradiance": 4, "multiple_scattering": 5}
+          "scattering_density": 3, "indirect_irradiance": 4, "multiple_scattering": 5,
+          "density_setup": 6}
 
 
 class PasError(RuntimeError):
