@@ -1,0 +1,11 @@
+// Scattering density kernel, channel pitch 4, multi-GPU (mirrored stores) instantiations.
+#include "kernel_density.cuh"
+
+namespace pas {
+namespace density {
+template cudaError_t launch_cp<4, true>(const PasGeometry& g, int nc, const PasDensityDir* dirs, const float* G,
+                                const float* cR, const float* cM, const float* dR, const float* dM,
+                                const float* dS, const float* dE, int order, float* dJ,
+                                const PeerTables& mirrors, LayerSet layers, cudaStream_t stream);
+}  // namespace density
+}  // namespace pas

@@ -9,7 +9,12 @@ The kernel does not do the reference's 4-D lookups. It relies on three facts (DE
      linear in the table values, so the per-direction work is a set of channel-independent weights;
   3. the cosine of the sun zenith angle at the ground point is affine in nu1:
      (r mu_s + d_ground nu1) / bottom, so the ground irradiance is a piecewise-linear ramp sum too.
-This test rebuilds one texel of the density table from those three statements, in plain numpy, and
+  4. omega_s is a unit vector, so over the 32 azimuths of one polar direction x stays inside
+     x0 +- A, x0 = (mu_s cos(theta) + 1)(NU - 1)/2, A = sin(theta) sqrt(1 - mu_s^2)(NU - 1)/2 -- an
+     interval shared by every texel of a (layer, mu_s column) block. Ramps below it are identically 1
+     and telescope into the base value V[lo]; ramps above it are identically 0: the kernel stages the
+     rows rebased at lo = floor(x0 - A) and sweeps only the live ramps.
+This test rebuilds one texel of the density table from those statements, in plain numpy, and
 compares it with the oracle (which loops over directions and calls the literal GetScattering /
 GetIrradiance / GetTransmittance). No GPU, no kernel code: it pins the formulation, not the port.
 """
@@ -123,3 +128,55 @@ def test_ramp_sum_is_the_clamped_linear_interpolation():
         i = min(int(math.floor(xc)), 6)
         want = V[:, i] + (xc - i) * (V[:, i + 1] - V[:, i])
         assert np.allclose(ramp_interp(V, x), want, rtol=1e-13)
+
+
+def window_of(mu_s, theta, nu_n, margin=1e-3):
+    """Statement 4, as csrc/kernel_density.cuh computes it per (block, direction): first knot and the
+    number of live ramps."""
+    sc = 0.5 * (nu_n - 1)
+    x0 = (mu_s * math.cos(theta) + 1.0) * sc
+    a = sc * math.sin(theta) * math.sqrt(max(1.0 - mu_s * mu_s, 0.0)) + margin
+    lo = min(max(math.floor(x0 - a), 0), nu_n - 2)
+    hi = min(max(math.ceil(x0 + a), lo + 1), nu_n - 1)
+    return lo, hi
+
+
+def test_ramp_window_is_block_uniform_and_the_rebased_sum_is_exact(world):
+    o = world[0]
+    R, MU, MUS, NU = SIZES["r"], SIZES["mu"], SIZES["mu_s"], SIZES["nu"]
+    rng = np.random.default_rng(3)
+    V = rng.uniform(0.1, 2.0, size=(3, NU))
+    D = np.diff(V, axis=1)
+    live_counts = []
+    for k in (0, 3, R - 1):
+        for i_mu_s in range(MUS):
+            mu_s_col = None
+            for l in range(16):
+                theta = (l + 0.5) * math.pi / 16
+                ct, st = math.cos(theta), math.sin(theta)
+                xs = []
+                for j in range(0, MU, 3):
+                    for i_nu in range(NU):
+                        r, mu, mu_s, nu, _ = o.rmumusnu_from_frag_coord(i_nu * MUS + i_mu_s + 0.5, j + 0.5, k + 0.5)
+                        mu_s_col = mu_s if mu_s_col is None else mu_s_col
+                        assert mu_s == mu_s_col                      # one mu_s per block
+                        wx = math.sqrt(1.0 - mu * mu)
+                        sx = 0.0 if wx == 0.0 else (nu - mu * mu_s) / wx
+                        sy = math.sqrt(max(1.0 - sx * sx - mu_s * mu_s, 0.0))
+                        for m in range(32):
+                            phi = (m + 0.5) * math.pi / 16
+                            nu1 = sx * math.cos(phi) * st + sy * math.sin(phi) * st + mu_s * ct
+                            xs.append((nu1 + 1.0) * 0.5 * (NU - 1))
+                xs = np.asarray(xs)
+                lo, hi = window_of(mu_s_col, theta, NU)
+                live_counts.append(hi - lo)
+                # every x of the block lies in [lo, hi] up to the clamping of the lookup itself
+                xc = np.clip(xs, 0.0, NU - 1.0)
+                assert xc.min() >= lo - 1e-9 and xc.max() <= hi + 1e-9, (k, i_mu_s, l, xs.min(), xs.max(), lo, hi)
+                # rebased ramp sum: base V[lo] + live ramps only == the full ramp sum
+                for x in xs[::97]:
+                    full = ramp_interp(V, x)
+                    reb = V[:, lo] + (D[:, lo:hi] * sat(x - lo - np.arange(hi - lo))[None, :]).sum(axis=1)
+                    assert np.allclose(reb, full, rtol=1e-13), (x, lo, hi)
+    assert 1 <= min(live_counts) and max(live_counts) == NU - 1
+    assert np.mean(live_counts) < NU - 1.5       # the window does cut work (5.0 of 7 at the reference's sizes)
