@@ -301,6 +301,22 @@ int pas_world_is_cached(int device, int rank, int world_size);
 pas_status pas_model_ipc_export(pas_model* model, int rank, int world_size, void* out, size_t* bytes);
 pas_status pas_model_attach_peers(pas_model* model, const void* all_exports, size_t bytes_per_rank);
 
+/* Symmetric-memory worlds (preferred where the host can provide one): every rank owns an arena of
+ * `bytes` bytes of device memory that every other rank of the box has mapped -- `arena_bases[r]` is rank
+ * r's arena as seen from THIS process (arena_bases[rank] = the local one) -- and, where the NVSwitch
+ * supports it, `multicast_base` is ONE address whose stores land in the arenas of all ranks at once
+ * (NVLS multicast; NULL = unicast stores to arena_bases). The host side allocates and maps the arenas
+ * (torch.distributed._symmetric_memory in world.py: CUDA VMM + fabric handles) ONCE per (rank, world)
+ * and hands them to every model it creates afterwards: attaching needs no collective. The arena holds
+ * the exchange copies of the model's tables (transmittance, two scattering-density buffers, irradiance
+ * partial sums, staging of the final scattering slabs) and the flag words of the barriers; it must be
+ * zero when first attached and at least pas_model_exchange_bytes() large. With multicast the density
+ * kernel sends each texel of its r-slab once instead of once per peer. Models that share an arena
+ * run their Inits one at a time (PAS_ERR_STATE otherwise); their product tables stay their own. */
+pas_status pas_model_exchange_bytes(const pas_model* model, int world_size, size_t* bytes);
+pas_status pas_model_attach_symmetric(pas_model* model, int rank, int world_size,
+                                      void* const* arena_bases, void* multicast_base, size_t bytes);
+
 /* Device memory of destroyed models is kept in a process-wide pool for the next pas_model_create
  * (the demo re-creates its Model on every settings change, atmosphere/demo/demo.cc:446-494);
  * this returns it to the driver. */

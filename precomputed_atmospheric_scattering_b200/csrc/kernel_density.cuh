@@ -669,7 +669,7 @@ cudaError_t launch_one(const PasGeometry& g, int nc, const PasDensityDir* dirs, 
     // measured on 8 / 4 / 2 B200 (15 channels): pairs of columns (128-byte runs) beat single columns
     // from 3 mirrors on (1.54 vs 1.69 ms, 2.31 vs 2.35 ms); clusters of 4 lose to the longer wait at
     // the cluster barrier (1.59 ms); with one mirror the plain layout wins (3.96 vs 4.08 ms)
-    const unsigned cl = (mirrors.n >= 3 && g.sz.mu_s_n % 2 == 0) ? 2 : 1;
+    const unsigned cl = ((mirrors.n >= 3 || mirrors.multicast) && g.sz.mu_s_n % 2 == 0) ? 2 : 1;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
     cfg.blockDim = dim3(threads);

@@ -30,6 +30,7 @@ struct FinalTables {
 struct PeerTables {
   int n;
   float* tab[PAS_MAX_PEERS];
+  int multicast;   // tab[0] is an NVLS multicast address: one store reaches every rank (the local copy too)
 };
 
 // The scattering layers a launch works on: begin, begin + stride, ... < end. One GPU: all of them.

@@ -222,14 +222,22 @@ struct DeviceBuffer {
   void* p = nullptr;
   size_t bytes = 0;
   int device = 0;
+  bool borrowed = false;   // points into memory owned by somebody else (a symmetric arena)
   ~DeviceBuffer() { release(); }
   void release() {
-    if (p) pool().give(device, bytes, p);
+    if (p && !borrowed) pool().give(device, bytes, p);
     p = nullptr;
     bytes = 0;
+    borrowed = false;
+  }
+  void adopt(void* ptr, size_t n) {
+    release();
+    p = ptr;
+    bytes = n;
+    borrowed = true;
   }
   cudaError_t ensure(size_t n) {
-    if (n <= bytes) return cudaSuccess;
+    if (n <= bytes && !borrowed) return cudaSuccess;
     release();
     cudaError_t e = cudaGetDevice(&device);
     if (e != cudaSuccess) return e;
@@ -350,6 +358,37 @@ struct pas_model {
   float* peer_xE[PAS_MAX_PEERS + 1] = {};
   unsigned* peer_flags[PAS_MAX_PEERS + 1] = {};
   unsigned exchanges = 0;          // orders exchanged so far: its parity selects dJ / dJ2 and the xE half
+  // symmetric-arena worlds (pas_model_attach_symmetric): T, dJ, dJ2, xE live in the arena; the final
+  // scattering slabs are exchanged through arena staging areas (the product tables stay the model's)
+  bool symm = false;
+  char* arena[PAS_MAX_PEERS + 1] = {};
+  char* arena_mc = nullptr;        // multicast address of the arenas, or nullptr
+  size_t off_T = 0, off_dJ[2] = {0, 0}, off_xE = 0, off_Sx = 0, off_Mx = 0;
+  // destinations of this rank's stores for an exchanged table at arena offset `off`: the one multicast
+  // address when there is one (it includes the local copy), else the table in every other rank's arena
+  pas::PeerTables mirrors_at(size_t off) const {
+    pas::PeerTables t{};
+    if (arena_mc != nullptr) {
+      t.tab[t.n++] = reinterpret_cast<float*>(arena_mc + off);
+      t.multicast = 1;
+    } else {
+      for (int r = 0; r < world; ++r) {
+        if (r != rank) t.tab[t.n++] = reinterpret_cast<float*>(arena[r] + off);
+      }
+    }
+    return t;
+  }
+  pas::PeerTargets targets_at(size_t off) const {
+    pas::PeerTargets t{};
+    if (arena_mc != nullptr) {
+      t.dst[t.n++] = arena_mc + off;
+    } else {
+      for (int r = 0; r < world; ++r) {
+        if (r != rank) t.dst[t.n++] = arena[r] + off;
+      }
+    }
+    return t;
+  }
 
   size_t n_t() const { return (size_t)geom.sz.t_w * geom.sz.t_h; }
   size_t n_e() const { return (size_t)geom.sz.e_w * geom.sz.e_h; }
@@ -593,6 +632,17 @@ pas_status allocate(pas_model* m) {
   return PAS_OK;
 }
 
+// A model leaving a symmetric arena (re-attached to another kind of world) gets buffers of its own back.
+pas_status leave_arena(pas_model* m) {
+  m->symm = false;
+  m->arena_mc = nullptr;
+  m->T.release();
+  m->dJ.release();
+  m->dJ2.release();
+  m->xE.release();
+  return allocate(m);
+}
+
 // One phase of Precompute (model.cc:1048-1215) for channel group `gi`.
 // Cross-GPU barrier on `stream`; channel 0 belongs to the main stream of Init, 1 to the side stream.
 // Entry points that read results first wait for an Init still in flight (pas_model_init_async).
@@ -630,8 +680,12 @@ pas_status run_phase(pas_model* m, int gi, int phase, int order, bool accumulate
       if (m->peer) {
         // a band of transmittance rows per rank, stored to every rank; then all meet
         pas::PeerTables mirrors{};
-        for (int r = 0; r < m->world; ++r) {
-          if (r != m->rank) mirrors.tab[mirrors.n++] = m->peer_T[r];
+        if (m->symm) {
+          mirrors = m->mirrors_at(m->off_T);
+        } else {
+          for (int r = 0; r < m->world; ++r) {
+            if (r != m->rank) mirrors.tab[mirrors.n++] = m->peer_T[r];
+          }
         }
         const int base = g.sz.t_h / m->world, extra = g.sz.t_h % m->world;
         const int j0 = m->rank * base + std::min(m->rank, extra);
@@ -669,7 +723,9 @@ pas_status run_phase(pas_model* m, int gi, int phase, int order, bool accumulate
       // this order's parity; the barrier comes with the irradiance partial sums (phase 4)
       pas::PeerTables mirrors{};
       const int par = (int)(m->exchanges & 1);
-      if (m->peer) {
+      if (m->symm) {
+        mirrors = m->mirrors_at(m->off_dJ[par]);
+      } else if (m->peer) {
         for (int r = 0; r < m->world; ++r) {
           if (r != m->rank) mirrors.tab[mirrors.n++] = m->peer_dJ[par][r];
         }
@@ -704,8 +760,12 @@ pas_status run_phase(pas_model* m, int gi, int phase, int order, bool accumulate
         PAS_CUDA(pas::launch_indirect_irradiance(g, sp, m->dR.f(), m->dM.f(), ds_in, order,
                                                  m->xE.f() + slot, fin, 0, g.sz.e_h, ks, stream));
         pas::PeerTargets t{};
-        for (int r = 0; r < m->world; ++r) {
-          if (r != m->rank) t.dst[t.n++] = m->peer_xE[r];
+        if (m->symm) {
+          t = m->targets_at(m->off_xE);
+        } else {
+          for (int r = 0; r < m->world; ++r) {
+            if (r != m->rank) t.dst[t.n++] = m->peer_xE[r];
+          }
         }
         PAS_CUDA(pas::launch_peer_push(m->xE.f(), m->n_e() * sp.nc * sizeof(float), slot * sizeof(float), t, stream));
         if (channel != 0) {
@@ -1128,10 +1188,16 @@ pas_status pas_model_init_async(pas_model* m, unsigned int num_scattering_orders
     const pas::LayerSet ks = m->layers();
     const size_t layer_bytes = m->layer_texels() * m->s_texel_bytes();
     pas::PeerTargets ts{}, tm{};
-    for (int r = 0; r < m->world; ++r) {
-      if (r == m->rank) continue;
-      ts.dst[ts.n++] = m->peer_S[r];
-      tm.dst[tm.n++] = m->peer_M[r];
+    if (m->symm) {
+      // the product tables are the model's own: the slabs travel through staging areas of the arena
+      ts = m->targets_at(m->off_Sx);
+      tm = m->targets_at(m->off_Mx);
+    } else {
+      for (int r = 0; r < m->world; ++r) {
+        if (r == m->rank) continue;
+        ts.dst[ts.n++] = m->peer_S[r];
+        tm.dst[tm.n++] = m->peer_M[r];
+      }
     }
     PAS_CUDA(pas::launch_peer_push(m->S.p, layer_bytes, (size_t)ks.begin * layer_bytes, ts, main, ks.count(),
                                    (size_t)ks.stride * layer_bytes));
@@ -1142,6 +1208,24 @@ pas_status pas_model_init_async(pas_model* m, unsigned int num_scattering_orders
     pas_status st = peer_barrier(m, 0, main);
     if (st != PAS_OK) return st;
     m->launches += m->combined ? 1 : 2;
+    if (m->symm) {
+      // the other ranks' layers: staging area -> product table (the own slab is already there)
+      const size_t lo = (size_t)ks.begin * layer_bytes, hi = (size_t)ks.end * layer_bytes;
+      const size_t all = (size_t)m->geom.sz.r_n * layer_bytes;
+      auto gather = [&](void* table, size_t off) -> cudaError_t {
+        const char* src = m->arena[m->rank] + off;
+        cudaError_t e = cudaSuccess;
+        if (lo > 0) e = cudaMemcpyAsync(table, src, lo, cudaMemcpyDeviceToDevice, main);
+        if (e == cudaSuccess && hi < all) {
+          e = cudaMemcpyAsync(static_cast<char*>(table) + hi, src + hi, all - hi, cudaMemcpyDeviceToDevice, main);
+        }
+        return e;
+      };
+      PAS_CUDA(gather(m->S.p, m->off_Sx));
+      if (!m->combined) PAS_CUDA(gather(m->M.p, m->off_Mx));
+      // the staging areas are rewritten by the next Init's final push: every rank must have read them
+      // first, which the first barrier of that Init (transmittance rows) guarantees
+    }
   } else if (m->world > 1) {
     // every rank ends with the complete scattering table(s)
     const pas::LayerSet ks = m->layers();
@@ -1426,8 +1510,13 @@ pas_status pas_model_attach_world(pas_model* m, int rank, int world_size, const 
     return fail(PAS_ERR_INVALID_ARGUMENT, "bad rank / world size");
   }
   if (world_size == 1) {
+    if (m->symm) {
+      pas_status st = leave_arena(m);
+      if (st != PAS_OK) return st;
+    }
     m->rank = 0;
     m->world = 1;
+    m->peer = false;
     return PAS_OK;
   }
   if (m->geom.sz.r_n % world_size != 0) {
@@ -1450,6 +1539,11 @@ pas_status pas_model_attach_world(pas_model* m, int rank, int world_size, const 
       cache.comms[key] = m->comm;
     }
   }
+  if (m->symm) {
+    // back to buffers of its own
+    pas_status st = leave_arena(m);
+    if (st != PAS_OK) return st;
+  }
   m->rank = rank;
   m->world = world_size;
   m->peer = false;  // a model attached to an NCCL world no longer uses a peer mapping it may have had
@@ -1469,6 +1563,13 @@ pas_status pas_model_ipc_export(pas_model* m, int rank, int world_size, void* ou
     return fail(PAS_ERR_UNSUPPORTED, "scattering_r must be divisible by the world size");
   }
   PAS_CUDA(cudaSetDevice(m->device));
+  if (m->symm) {
+    pas_status st = leave_arena(m);
+    if (st != PAS_OK) return st;
+    m->peer = false;
+    m->world = 1;
+    m->rank = 0;
+  }
   // rank and world take effect in pas_model_attach_peers, once every mapping has succeeded
   m->pending_rank = rank;
   m->pending_world = world_size;
@@ -1565,6 +1666,106 @@ pas_status pas_model_attach_peers(pas_model* m, const void* exports, size_t byte
   m->rank = rank;
   m->world = world;
   m->peer = true;
+  m->exchanges = 0;
+  return PAS_OK;
+}
+
+namespace {
+// Layout of a model's exchange tables inside a symmetric arena: flag words first (fixed place, whatever
+// the model), then the tables, each aligned to 1 KiB.
+struct ArenaLayout {
+  size_t flags = 0, T = 0, dJ[2] = {0, 0}, xE = 0, Sx = 0, Mx = 0, bytes = 0;
+};
+ArenaLayout arena_layout(const pas_model* m, int world) {
+  ArenaLayout a;
+  size_t at = 4096;  // PAS_FLAG_CHANNELS x PAS_FLAG_WORDS words, generously
+  auto take = [&](size_t n) {
+    const size_t here = at;
+    at += (n + 1023) / 1024 * 1024;
+    return here;
+  };
+  const size_t cp = PAS_CHANNEL_PITCH(m->max_nc());
+  a.T = take(m->n_t() * cp * sizeof(float));
+  a.dJ[0] = take(m->n_s() * cp * sizeof(float));
+  a.dJ[1] = take(m->n_s() * cp * sizeof(float));
+  a.xE = take((size_t)2 * world * m->xe_stride() * sizeof(float));
+  a.Sx = take(m->n_s() * m->s_texel_bytes());
+  a.Mx = m->combined ? a.Sx : take(m->n_s() * m->s_texel_bytes());
+  a.bytes = at;
+  return a;
+}
+}  // namespace
+
+pas_status pas_model_exchange_bytes(const pas_model* m, int world_size, size_t* bytes) {
+  if (m == nullptr || bytes == nullptr) return fail(PAS_ERR_INVALID_ARGUMENT, "NULL argument");
+  if (world_size < 2 || world_size > PAS_MAX_PEERS + 1) {
+    return fail(PAS_ERR_INVALID_ARGUMENT, "symmetric worlds have 2..8 ranks");
+  }
+  *bytes = arena_layout(m, world_size).bytes;
+  return PAS_OK;
+}
+
+pas_status pas_model_attach_symmetric(pas_model* m, int rank, int world_size, void* const* arena_bases,
+                                      void* multicast_base, size_t bytes) {
+  if (m == nullptr || arena_bases == nullptr) return fail(PAS_ERR_INVALID_ARGUMENT, "NULL argument");
+  if (world_size < 2 || world_size > PAS_MAX_PEERS + 1 || rank < 0 || rank >= world_size) {
+    return fail(PAS_ERR_INVALID_ARGUMENT, "symmetric worlds have 2..8 ranks");
+  }
+  if (m->geom.sz.r_n % world_size != 0) {
+    return fail(PAS_ERR_UNSUPPORTED, "scattering_r must be divisible by the world size");
+  }
+  { pas_status settled = settle(m); if (settled != PAS_OK) return settled; }
+  const ArenaLayout a = arena_layout(m, world_size);
+  if (bytes < a.bytes) {
+    return fail(PAS_ERR_INVALID_ARGUMENT, "arena of " + std::to_string(bytes) + " bytes, this model needs " +
+                                              std::to_string(a.bytes));
+  }
+  for (int r = 0; r < world_size; ++r) {
+    if (arena_bases[r] == nullptr) return fail(PAS_ERR_INVALID_ARGUMENT, "NULL arena base");
+  }
+  PAS_CUDA(cudaSetDevice(m->device));
+  {
+    // one barrier sequence per (device, rank, world) and kind of world; the flag words (and with them
+    // the epoch counters) live in the arena, so a new, zeroed arena restarts the sequence on every rank
+    PeerCache& cache = peer_cache();
+    std::lock_guard<std::mutex> lock(cache.mu);
+    PeerWorld& w = cache.worlds[std::make_tuple(m->device, rank, world_size | 0x100)];
+    if (w.error_host == nullptr) {
+      PAS_CUDA(cudaHostAlloc(&w.error_host, sizeof(int), cudaHostAllocMapped));
+      *w.error_host = 0;
+      PAS_CUDA(cudaHostGetDevicePointer(&w.error_dev, w.error_host, 0));
+    }
+    if (w.in_flight != nullptr && w.in_flight != m) {
+      return fail(PAS_ERR_STATE, "another model of this world has an Init in flight: wait for it first");
+    }
+    if (w.flags != static_cast<unsigned*>(arena_bases[rank])) {
+      w.flags = static_cast<unsigned*>(arena_bases[rank]);  // a new arena: a fresh barrier sequence
+      w.broken = false;
+    }
+    m->pw = &w;
+  }
+  for (int r = 0; r < world_size; ++r) {
+    m->arena[r] = static_cast<char*>(arena_bases[r]);
+    m->peer_flags[r] = reinterpret_cast<unsigned*>(m->arena[r] + a.flags);
+  }
+  m->arena_mc = static_cast<char*>(multicast_base);
+  m->off_T = a.T;
+  m->off_dJ[0] = a.dJ[0];
+  m->off_dJ[1] = a.dJ[1];
+  m->off_xE = a.xE;
+  m->off_Sx = a.Sx;
+  m->off_Mx = a.Mx;
+  const size_t cp = PAS_CHANNEL_PITCH(m->max_nc());
+  char* mine = m->arena[rank];
+  m->T.adopt(mine + a.T, m->n_t() * cp * sizeof(float));
+  m->dJ.adopt(mine + a.dJ[0], m->n_s() * cp * sizeof(float));
+  m->dJ2.adopt(mine + a.dJ[1], m->n_s() * cp * sizeof(float));
+  m->xE.adopt(mine + a.xE, (size_t)2 * world_size * m->xe_stride() * sizeof(float));
+  m->rank = rank;
+  m->world = world_size;
+  m->peer = true;
+  m->symm = true;
+  m->comm = nullptr;
   m->exchanges = 0;
   return PAS_OK;
 }

@@ -119,6 +119,9 @@ def load_library() -> ctypes.CDLL:
         lib.pas_world_is_cached.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int]
         lib.pas_model_ipc_export.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.POINTER(ctypes.c_size_t)]
         lib.pas_model_attach_peers.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]
+        lib.pas_model_exchange_bytes.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_size_t)]
+        lib.pas_model_attach_symmetric.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
+                                                   ctypes.POINTER(ctypes.c_void_p), ctypes.c_void_p, ctypes.c_size_t]
         lib.pas_release_cached_memory.restype = None
         _FP = ctypes.POINTER(ctypes.c_float)
         lib.pas_model_get_solar_radiance.argtypes = [ctypes.c_void_p, ctypes.c_int, _DP]
@@ -495,6 +498,20 @@ class Model:
         buf = ctypes.create_string_buffer(IPC_EXPORT_BYTES)
         _check(self._lib.pas_model_ipc_export(self._h, rank, world_size, buf, ctypes.byref(n)))
         return buf.raw[:n.value]
+
+    def exchange_bytes(self, world_size: int) -> int:
+        """Size of the symmetric arena this model needs in a world of ``world_size`` ranks."""
+        n = ctypes.c_size_t()
+        _check(self._lib.pas_model_exchange_bytes(self._h, int(world_size), ctypes.byref(n)))
+        return n.value
+
+    def attach_symmetric(self, rank: int, world_size: int, arena_ptrs: Sequence[int], multicast_ptr: int,
+                         arena_bytes: int) -> None:
+        """pas_model_attach_symmetric: ``arena_ptrs[r]`` = rank r's arena mapped in this process,
+        ``multicast_ptr`` = the NVLS multicast address of the arenas (0 = none)."""
+        bases = (ctypes.c_void_p * world_size)(*[int(p) for p in arena_ptrs])
+        _check(self._lib.pas_model_attach_symmetric(self._h, int(rank), int(world_size), bases,
+                                                    ctypes.c_void_p(int(multicast_ptr) or None), int(arena_bytes)))
 
     def attach_peers(self, exports: bytes, bytes_per_rank: int = 0) -> None:
         """Maps the other ranks' buffers: ``exports`` = the ranks' ``ipc_export`` blobs in rank order."""

@@ -1,14 +1,18 @@
 """Multi-GPU plumbing: one process per GPU, rendezvous through ``torch.distributed``.
 
-The compute and the NVLink exchange live in libpas_b200.so (r-slab sharding of every 3-D pass). Two
-exchanges are built (include/pas_b200.h):
-  * ``peer`` (default): the scattering-density kernel stores its r-slab straight into the other
-    ranks' tables (CUDA IPC mappings), irradiance partial sums and final slabs are pushed the same
-    way, ranks meet at flag barriers in device memory -- no collective library on the data path;
+The compute and the NVLink exchange live in libpas_b200.so (r-slab sharding of every 3-D pass). Three
+exchanges are built (include/pas_b200.h), tried in this order:
+  * ``symm`` (default): a symmetric arena per rank (torch.distributed._symmetric_memory: CUDA VMM
+    allocations mapped by every rank, plus -- on NVSwitch boxes -- one NVLS multicast address for all
+    of them), allocated ONCE per (rank, world) and shared by every model attached afterwards, so that
+    attaching a model costs no collective. The scattering-density kernel stores its r-slab through
+    the multicast address: one store reaches every rank. Flag barriers in device memory;
+  * ``peer``: the same kernels over CUDA IPC mappings of each model's own buffers (one all-gather of
+    464 bytes per rank and model), unicast stores to every peer;
   * ``nccl``: all-gather of the density slabs / all-reduce of the irradiance partial sums.
-What is left for the host is to move a few hundred bytes once per model -- the ranks' IPC handles
-(or an NCCL unique id) -- and to agree on who owns which r-layers; that is all this module does. It
-works with any torch.distributed backend (``nccl`` on the GPU box, ``gloo`` in the CPU tests).
+What is left for the host is to set up those mappings (or an NCCL unique id) and to agree on who
+owns which r-layers; that is all this module does. It works with any torch.distributed backend
+(``nccl`` on the GPU box, ``gloo`` in the CPU tests).
 """
 from __future__ import annotations
 
@@ -21,6 +25,32 @@ import torch.distributed as dist
 
 UNIQUE_ID_BYTES = 128  # PAS_NCCL_UNIQUE_ID_BYTES
 _PEER_WORLDS = set()   # (rank, world) for which this process has agreed on the peer exchange
+_ARENAS = {}           # (rank, world) -> Arena: the symmetric arena of this process in that world
+_NO_SYMM = set()       # (rank, world) for which the symmetric exchange was tried and is unavailable
+
+
+class Arena:
+    """A symmetric arena: ``ptrs[r]`` = rank r's arena mapped in this process, ``multicast`` = the
+    NVLS multicast address of all of them (0 = none), ``keep`` = whatever owns the memory."""
+
+    def __init__(self, ptrs, multicast, nbytes, keep=None):
+        self.ptrs, self.multicast, self.nbytes, self.keep = list(ptrs), int(multicast or 0), int(nbytes), keep
+
+
+def allocate_arena(nbytes: int, group=None) -> Arena:
+    """COLLECTIVE: allocates ``nbytes`` of zeroed symmetric memory on every rank and maps every rank's
+    allocation into every process (torch.distributed._symmetric_memory). Raises where the platform has
+    no symmetric memory (no peer access, no fabric handles, a CPU-only process group)."""
+    import torch.distributed._symmetric_memory as symm_mem
+    device = torch.device("cuda", torch.cuda.current_device())
+    group = group if group is not None else dist.group.WORLD
+    t = symm_mem.empty(int(nbytes), dtype=torch.uint8, device=device)
+    h = symm_mem.rendezvous(t, group)
+    t.zero_()
+    torch.cuda.synchronize()
+    dist.barrier(group)      # nobody signals a flag word before every arena is zero
+    multicast = h.multicast_ptr if os.environ.get("PAS_MULTICAST", "1") != "0" else 0
+    return Arena(h.buffer_ptrs, multicast, nbytes, keep=(t, h))
 
 
 def slab(r_n: int, rank: int, world: int) -> Tuple[int, int]:
@@ -76,14 +106,46 @@ def all_gather_bytes(blob: bytes, group=None, device: Optional[torch.device] = N
 
 def attach(model, group=None, exchange: Optional[str] = None) -> Tuple[int, int]:
     """Attaches ``model`` (model.Model) to the default process group: returns (rank, world).
-    ``exchange``: "peer" (default; env PAS_EXCHANGE overrides) or "nccl"."""
+    ``exchange``: "symm" (default; env PAS_EXCHANGE overrides), "peer" or "nccl"; an exchange that the
+    box cannot provide falls through to the next one on every rank together, unless it was asked for
+    explicitly."""
     from .model import nccl_unique_id, world_is_cached
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     if world == 1:
         model.attach_world(0, 1, None)
         return rank, world
     requested = exchange or os.environ.get("PAS_EXCHANGE")
-    exchange = requested or "peer"
+    exchange = requested or "symm"
+    if exchange == "symm":
+        if (rank, world) not in _NO_SYMM:
+            need = model.exchange_bytes(world)
+            arena = _ARENAS.get((rank, world))
+            if arena is None or arena.nbytes < need:
+                # every rank creates the same models in the same order, so every rank is here together:
+                # allocate (with headroom, so that a slightly larger model does not allocate again) and
+                # agree that it worked everywhere
+                arena, error = None, None
+                try:
+                    arena = allocate_arena(max(need + need // 8, 1 << 20), group)
+                except Exception as e:
+                    error = e
+                if _all_ok(error is None, group):
+                    _ARENAS[(rank, world)] = arena
+                else:
+                    arena = None
+                    _NO_SYMM.add((rank, world))
+                    if requested == "symm":
+                        raise error if error is not None else RuntimeError(
+                            "another rank could not allocate its symmetric arena")
+                    warnings.warn(f"symmetric-memory exchange unavailable ({error or 'on another rank'}): "
+                                  "using CUDA IPC peer mappings")
+            if arena is not None:
+                # no collective from here on: the arena is mapped, the model only takes its tables in it
+                model.attach_symmetric(rank, world, arena.ptrs, arena.multicast, arena.nbytes)
+                return rank, world
+        elif requested == "symm":
+            raise RuntimeError("the symmetric-memory exchange is unavailable in this world")
+        exchange = "peer"
     if exchange == "peer":
         # Every rank must end up on the same exchange: a rank whose GPU cannot export or map peer
         # memory (no P2P between the devices, IPC disabled in the container) tells the others, and
@@ -126,7 +188,7 @@ def attach(model, group=None, exchange: Optional[str] = None) -> Tuple[int, int]
             raise error if error is not None else RuntimeError("another rank could not set up the peer exchange")
         warnings.warn(f"peer-memory exchange unavailable ({error or 'on another rank'}): using NCCL")
     elif exchange != "nccl":
-        raise ValueError("exchange must be 'peer' or 'nccl'")
+        raise ValueError("exchange must be 'symm', 'peer' or 'nccl'")
     device = model.device if model.device is not None else torch.cuda.current_device()
     # the library keeps one communicator per (device, rank, world) for the life of the process;
     # every rank takes the same branch because every rank has attached the same number of models

@@ -1,5 +1,6 @@
 """Multi-GPU parity: r-slab sharding over 2 (or more) B200s with the exchange inside the library --
-peer-memory stores fused into the density kernel + flag barriers, or NCCL collectives -- must give
+stores fused into the density kernel (through the NVLS multicast address of a symmetric arena, or
+unicast into CUDA IPC mappings) + flag barriers, or NCCL collectives -- must give
 the single-GPU tables bit for bit (same kernels, same per-texel order of operations; the exchange
 only moves data), except the irradiance, whose per-slab partial sums are added in a different order
 (compared at 1e-6). Skipped with fewer than 2 GPUs."""
@@ -20,6 +21,19 @@ def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         return s.getsockname()[1]
+
+
+def _spawn(fn, world_size, *args):
+    """mp.spawn on a free rendezvous port; a port that another process grabbed in between (EADDRINUSE)
+    is not a test failure: try another one."""
+    import torch.multiprocessing as mp
+    for attempt in range(4):
+        try:
+            mp.spawn(fn, args=(world_size, _free_port()) + args, nprocs=world_size, join=True)
+            return
+        except Exception as e:  # ProcessRaisedException carries the child's traceback as text
+            if "EADDRINUSE" not in str(e) or attempt == 3:
+                raise
 
 
 def _worker(rank, world_size, port, out_dir, full_size, exchange):
@@ -47,7 +61,7 @@ def _worker(rank, world_size, port, out_dir, full_size, exchange):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("exchange", ["peer", "nccl"])
+@pytest.mark.parametrize("exchange", ["symm", "peer", "nccl"])
 @pytest.mark.parametrize("full_size", [False, True], ids=["small", "earth15"])
 @pytest.mark.timeout(600)
 def test_two_gpus_match_one(tmp_path, pas, full_size, exchange):
@@ -57,9 +71,7 @@ def test_two_gpus_match_one(tmp_path, pas, full_size, exchange):
     world_size = int(os.environ.get("PAS_TEST_WORLD", "2"))
     if n < world_size:
         pytest.skip(f"needs >= {world_size} GPUs")
-    import torch.multiprocessing as mp
-    mp.spawn(_worker, args=(world_size, _free_port(), str(tmp_path), full_size, exchange), nprocs=world_size,
-             join=True)
+    _spawn(_worker, world_size, str(tmp_path), full_size, exchange)
     spec = pas.earth(15, half_precision=False) if full_size else pas.small_planet()
     single = pas.Model.from_spec(spec, device=0, **({} if full_size else dict(sizes=SIZES)))
     single.Init(4)
@@ -74,7 +86,7 @@ def test_two_gpus_match_one(tmp_path, pas, full_size, exchange):
     single.close()
 
 
-def _variant_worker(rank, world_size, port, out_dir):
+def _variant_worker(rank, world_size, port, out_dir, exchange):
     import torch.distributed as dist
 
     import precomputed_atmospheric_scattering_b200 as pas
@@ -86,7 +98,7 @@ def _variant_worker(rank, world_size, port, out_dir):
     try:
         for name, spec, orders, sizes in _variants(pas):
             model = pas.Model.from_spec(spec, device=rank, **sizes)
-            world.attach(model, exchange="peer")
+            world.attach(model, exchange=exchange)
             model.Init(orders)
             out = dict(S=model.scattering, E=model.irradiance, T=model.transmittance)
             if not spec.combine_scattering_textures:
@@ -98,8 +110,8 @@ def _variant_worker(rank, world_size, port, out_dir):
         # has been waited for, it runs and gives the same tables
         a = pas.Model.from_spec(pas.small_planet(), device=rank, sizes=SIZES)
         b = pas.Model.from_spec(pas.small_planet(), device=rank, sizes=SIZES)
-        world.attach(a, exchange="peer")
-        world.attach(b, exchange="peer")
+        world.attach(a, exchange=exchange)
+        world.attach(b, exchange=exchange)
         a.InitAsync(3)
         try:
             b.InitAsync(3)
@@ -107,8 +119,11 @@ def _variant_worker(rank, world_size, port, out_dir):
         except pas.PasError as e:
             assert e.status == 5, e     # PAS_ERR_STATE
         a.Wait()
+        Sa, Ea = a.scattering, a.irradiance
         b.Init(3)
-        assert np.array_equal(a.scattering, b.scattering) and np.array_equal(a.irradiance, b.irradiance)
+        # (the product tables are each model's own, also when the models share a symmetric arena)
+        assert np.array_equal(Sa, b.scattering) and np.array_equal(Ea, b.irradiance)
+        assert np.array_equal(Sa, a.scattering)
         a.close()
         b.close()
         dist.barrier()
@@ -134,12 +149,12 @@ def _variants(pas):
             ("two_groups_full_size_single_order", pas.earth(24, half_precision=False), 1, {})]
 
 
+@pytest.mark.parametrize("exchange", ["symm", "peer"])
 @pytest.mark.timeout(600)
-def test_peer_exchange_variants(tmp_path, pas):
+def test_peer_exchange_variants(tmp_path, pas, exchange):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs >= 2 GPUs")
-    import torch.multiprocessing as mp
-    mp.spawn(_variant_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    _spawn(_variant_worker, 2, str(tmp_path), exchange)
     for name, spec, orders, sizes in _variants(pas):
         single = pas.Model.from_spec(spec, device=0, **sizes)
         single.Init(orders)

@@ -54,6 +54,53 @@ def _worker(rank, world_size, port, out_dir):
             def attach_world(self, r, w, uid):
                 self.calls.append(("world", r, w, uid))
 
+            def exchange_bytes(self, w):
+                return 3 << 20
+
+            def attach_symmetric(self, r, w, ptrs, mc, nbytes):
+                self.calls.append(("symm", r, w, tuple(ptrs), mc, nbytes))
+
+        # 1b'. the symmetric exchange: the arena is allocated once per (rank, world) -- a collective --
+        # and every later model attaches to it without one; a rank that cannot allocate takes every
+        # rank to the next exchange together
+        allocations = []
+
+        def fake_arena(nbytes, group=None):
+            allocations.append(nbytes)
+            return world.Arena([0x1000 * (r + 1) for r in range(world_size)], 0xabc000, nbytes)
+
+        real_alloc, world.allocate_arena = world.allocate_arena, fake_arena
+        try:
+            fm = FakeModel()
+            assert world.attach(fm, exchange="symm") == (rank, world_size)
+            assert fm.calls == [("symm", rank, world_size, tuple(0x1000 * (r + 1) for r in range(world_size)),
+                                 0xabc000, allocations[0])] and allocations[0] >= 3 << 20
+            fm = FakeModel()
+            assert world.attach(fm) == (rank, world_size) and len(allocations) == 1   # cached arena, default exchange
+            assert fm.calls[0][0] == "symm"
+
+            class Bigger(FakeModel):
+                def exchange_bytes(self, w):
+                    return 64 << 20
+
+            assert world.attach(Bigger()) == (rank, world_size) and len(allocations) == 2 and allocations[1] >= 64 << 20
+        finally:
+            world.allocate_arena = real_alloc
+            world._ARENAS.clear()
+        # no CUDA here: the real allocator fails on every rank, the default exchange falls through to peer
+        import warnings as _w
+        fm = FakeModel()
+        with _w.catch_warnings():
+            _w.simplefilter("ignore")
+            assert world.attach(fm) == (rank, world_size)
+        assert fm.calls[0][0] == "export" and (rank, world_size) in world._NO_SYMM
+        try:
+            world.attach(FakeModel(), exchange="symm")
+            raise AssertionError("explicit symmetric exchange fell back")
+        except RuntimeError:
+            pass
+        world._PEER_WORLDS.clear()
+
         fm = FakeModel()
         assert world.attach(fm, exchange="peer") == (rank, world_size)
         assert fm.calls[0] == ("export", rank, world_size)
