@@ -33,8 +33,9 @@ is the default.
 
 --impl reference times that CPU reference alone (rank 0 only under torchrun).
 Multi-GPU (torchrun, one rank per GPU): r-slab sharding inside the library; the density kernel stores
-its slab to every rank over NVLink peer memory, flag barriers between orders; strong scaling (the job
-is fixed, N GPUs share it).
+its slab to every rank through the NVLS multicast address of a symmetric arena (fallbacks: unicast
+CUDA IPC peer mappings, NCCL), flag barriers between orders; strong scaling (the job is fixed, N GPUs
+share it).
 """
 from __future__ import annotations
 
@@ -86,7 +87,9 @@ def config_dict(cfg_id: int, world_size: int) -> dict:
             "parallelism": "1 GPU" if world_size == 1 else (
                 f"r-slabs over {world_size} GPUs, " + ("NCCL all-gather / all-reduce per order"
                 if os.environ.get("PAS_EXCHANGE") == "nccl" else
-                "density slabs stored to all ranks by the kernel over NVLink peer memory, flag barriers")),
+                "density slabs stored to all ranks by the kernel " +
+                ("into CUDA IPC peer mappings (unicast)" if os.environ.get("PAS_EXCHANGE") == "peer" else
+                 "through the NVLS multicast address of a symmetric arena") + ", flag barriers")),
             "l2": "no flush between steps: every step recomputes and rewrites all tables "
                   "(5 x 60 MiB intermediates + products > 126 MB L2), nothing is reused across steps"}
 
@@ -395,12 +398,20 @@ def run_b200(args, rank, world_size, local_rank):
     # ---- e2e: host arrays -> Model -> Init -> host tables, every step -------------------------------
     info = {w: model.texture_info(w) for w in (pas.TEXTURE_TRANSMITTANCE, pas.TEXTURE_SCATTERING,
                                                pas.TEXTURE_IRRADIANCE)}
-    host = {}
-    for w, i in info.items():
-        shape = ((i.depth,) if i.depth > 1 else ()) + (i.height, i.width, 4)
-        dtype = np.float16 if i.bytes_per_channel == 2 else np.float32
-        t = torch.empty(shape, dtype=torch.float16 if dtype == np.float16 else torch.float32).pin_memory()
-        host[w] = t.numpy()
+    host, shared = {}, None
+    own_layers = distributed and os.environ.get("PAS_EXCHANGE", "symm") != "nccl" and \
+        os.environ.get("PAS_HOST_TABLES", "shared") == "shared"
+    if own_layers:
+        # N > 1: ONE set of page-locked host tables shared by the ranks (POSIX shared memory); every rank
+        # copies the layers it computed into it, Init returns once every rank's part is there
+        shared = world.shared_host_tables(model, list(info))
+        host = dict(shared.arrays)
+    else:
+        for w, i in info.items():
+            shape = ((i.depth,) if i.depth > 1 else ()) + (i.height, i.width, 4)
+            dtype = np.float16 if i.bytes_per_channel == 2 else np.float32
+            t = torch.empty(shape, dtype=torch.float16 if dtype == np.float16 else torch.float32).pin_memory()
+            host[w] = t.numpy()
     d2h = sum(a.nbytes for a in host.values())
     # parameters handed to the library per step: 7 spectra + wavelengths (48 doubles each), layers, scalars
     h2d = 8 * len(spec.wavelengths) * 8 + 5 * 5 * 8 + 12 * 8
@@ -412,6 +423,8 @@ def run_b200(args, rank, world_size, local_rank):
         m = new_model()
         m.set_host_outputs(transmittance=host[pas.TEXTURE_TRANSMITTANCE], scattering=host[pas.TEXTURE_SCATTERING],
                            irradiance=host[pas.TEXTURE_IRRADIANCE])
+        if own_layers:
+            m.set_host_output_mode(True)
         m.Init(ORDERS)
         L = m.luminance_matrix()
         m.close()
@@ -419,8 +432,10 @@ def run_b200(args, rank, world_size, local_rank):
 
     for _ in range(3):
         e2e_step()
-    for a in host.values():
-        a[...] = 0
+    barrier()
+    if not own_layers or rank == 0:
+        for a in host.values():
+            a[...] = 0
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
@@ -435,6 +450,9 @@ def run_b200(args, rank, world_size, local_rank):
         ok2 = int(round(world_size - world.sum_over_ranks(0.0 if p2["ok"] else 1.0))) == world_size
         parity["ok"] = bool(parity["ok"] and ok2)
 
+    if shared is not None:
+        host = {}
+        shared.close()
     if rank != 0:
         return 0 if (parity is None or parity["ok"]) else 3
     # ---- roofline of the dominant kernel ------------------------------------------------------------
@@ -512,7 +530,8 @@ def run_b200(args, rank, world_size, local_rank):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": config_dict(args.config, world_size),
         "e2e": {"value": round(e2e_ms, 4), "unit": "ms", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "what": "Model(host arrays) + Init with T, S, E copied into registered pinned host buffers as they become final + destroy"},
+                "what": "Model(host arrays) + Init with T, S, E copied into registered pinned host buffers as they become final + destroy"
+                        + ("; one set of host tables shared by the ranks, every rank copies the layers it computed" if own_layers else "")},
         "gpu_launches": launches, "clocks": clocks, "parity": parity, "roofline": roofline,
         "phases_ms": {k: round(v, 4) for k, v in phases.items()},
     }

@@ -128,6 +128,14 @@ pas_status pas_model_wait(pas_model* model);
  * buffers are valid when pas_model_init / pas_model_wait returns. Pass four NULLs to unregister. */
 pas_status pas_model_set_host_outputs(pas_model* model, void* transmittance, void* scattering,
                                       void* single_mie, void* irradiance);
+/* Multi-GPU worlds over peer / symmetric memory: with own_layers_only != 0 a rank copies out only the
+ * scattering layers it computed (rank 0 also the transmittance and irradiance tables), pipelined behind
+ * its passes like on one GPU, and the last cross-rank barrier of Init comes after those copies. The
+ * registered buffers are then meant to be ONE set of host tables shared by the ranks of the box (POSIX
+ * shared memory registered with cudaHostRegister by every rank, world.py: shared_host_tables): when
+ * Init returns on any rank, every layer of every table is in it. Default 0: every rank copies out
+ * complete tables after the final exchange. */
+pas_status pas_model_set_host_output_mode(pas_model* model, int own_layers_only);
 
 pas_status pas_model_texture_info(const pas_model* model, pas_texture which,
                                   pas_texture_info* info);

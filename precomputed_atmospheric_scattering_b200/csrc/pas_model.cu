@@ -331,6 +331,7 @@ struct pas_model {
   cudaStream_t copy = nullptr;
   cudaEvent_t ev_copy = nullptr;
   void* host_out[4] = {nullptr, nullptr, nullptr, nullptr};  // indexed by pas_texture
+  bool host_own_layers = false;     // multi-GPU: copy out only the layers this rank computed (shared host buffers)
   DeviceBuffer T, dE, dR, dM, dJ, dS, dirs, G, cR, cM, T_rgb, scratch;
   DeviceBuffer S, M, E, T_rgba;
   DeviceBuffer render_in[4], render_out[2];  // staging of host-pointer render queries
@@ -800,7 +801,6 @@ pas_status run_phase(pas_model* m, int gi, int phase, int order, bool accumulate
     case 5:
       PAS_CUDA(pas::launch_multiple_scattering(g, sp, m->T.f(), m->cur_dJ(), ds_out, fin, ks, stream));
       m->launches += 1;
-      if (m->peer) m->exchanges += 1;  // the next order uses the other density buffer / xE half
       break;
     case 6:
       // test hook: the per-(layer, direction) tables of the density pass alone, from whatever the
@@ -1004,6 +1004,13 @@ pas_status pas_model_set_host_outputs(pas_model* m, void* transmittance, void* s
   return PAS_OK;
 }
 
+pas_status pas_model_set_host_output_mode(pas_model* m, int own_layers_only) {
+  if (m == nullptr) return fail(PAS_ERR_INVALID_ARGUMENT, "model is NULL");
+  { pas_status settled = settle(m); if (settled != PAS_OK) return settled; }
+  m->host_own_layers = own_layers_only != 0;
+  return PAS_OK;
+}
+
 pas_status pas_model_wait(pas_model* m) {
   if (m == nullptr) return fail(PAS_ERR_INVALID_ARGUMENT, "model is NULL");
   if (!m->in_flight) return PAS_OK;
@@ -1072,8 +1079,13 @@ pas_status pas_model_init_async(pas_model* m, unsigned int num_scattering_orders
   // host as soon as its last writer is done -- T after the first pass, the single-Mie table after
   // single scattering, E after the last irradiance pass, S in four bands of layers behind the four
   // launches the last multiple-scattering pass is split into.
-  const bool pipe_out = !m->capture && m->world == 1 &&
+  // Peer worlds with pas_model_set_host_output_mode(own layers only): every rank copies the layers of
+  // the 3-D tables IT computed (rank 0 also T and E) into host buffers the ranks share, and the last
+  // barrier of Init comes after those copies: when Init returns on any rank, the whole table is there.
+  const bool pipe_out = !m->capture && (m->world == 1 || (m->peer && m->host_own_layers)) &&
                         (m->host_out[0] || m->host_out[1] || m->host_out[2] || m->host_out[3]);
+  const pas::LayerSet own = m->layers();
+  const bool lead = m->world == 1 || m->rank == 0;   // copies the 2-D tables
   auto copy_after = [&](cudaStream_t producer, int which, size_t offset, size_t bytes) -> cudaError_t {
     if (m->host_out[which] == nullptr || bytes == 0) return cudaSuccess;
     const DeviceBuffer* buf = nullptr;
@@ -1111,7 +1123,7 @@ pas_status pas_model_init_async(pas_model* m, unsigned int num_scattering_orders
       PAS_CUDA(pas::launch_pack_rgba(m->T.f(), (int)m->n_t(), 3, m->T_rgba.f(), main));
       m->launches += 1;
     }
-    if (pipe_out && gi == 0 && (fused_rgb || m->num_precomputed_wavelengths <= 3)) {
+    if (pipe_out && lead && gi == 0 && (fused_rgb || m->num_precomputed_wavelengths <= 3)) {
       PAS_CUDA(copy_after(main, PAS_TEXTURE_TRANSMITTANCE, 0, m->n_t() * 16));
     }
     timer.mark("transmittance");
@@ -1123,9 +1135,11 @@ pas_status pas_model_init_async(pas_model* m, unsigned int num_scattering_orders
     const bool last_group = gi + 1 == m->groups.size();
     if (pipe_out && last_group) {
       // the single-Mie table is written by single scattering only (model.cc:151-156)
-      PAS_CUDA(copy_after(main, PAS_TEXTURE_SINGLE_MIE, 0, m->n_s() * m->s_texel_bytes()));
+      const size_t layer_bytes = m->layer_texels() * m->s_texel_bytes();
+      PAS_CUDA(copy_after(main, PAS_TEXTURE_SINGLE_MIE, (size_t)own.begin * layer_bytes, (size_t)own.count() * layer_bytes));
       if (num_scattering_orders == 1) {
-        PAS_CUDA(copy_after(main, PAS_TEXTURE_SCATTERING, 0, m->n_s() * m->s_texel_bytes()));
+        PAS_CUDA(copy_after(main, PAS_TEXTURE_SCATTERING, (size_t)own.begin * layer_bytes,
+                            (size_t)own.count() * layer_bytes));
       }
     }
     timer.mark("single_scattering");
@@ -1155,11 +1169,11 @@ pas_status pas_model_init_async(pas_model* m, unsigned int num_scattering_orders
       if ((st = capture_copy(m, "delta_density_" + tag, m->cur_dJ(), m->n_s(), nc, off, true)) != PAS_OK) return st;
       if (pipe_out && last_group && order == num_scattering_orders) {
         // E is final (side stream); S becomes final band by band
-        PAS_CUDA(copy_after(side, PAS_TEXTURE_IRRADIANCE, 0, m->n_e() * 16));
-        const int r_n = m->geom.sz.r_n, parts = r_n >= 8 ? 4 : 1;
+        if (lead) PAS_CUDA(copy_after(side, PAS_TEXTURE_IRRADIANCE, 0, m->n_e() * 16));
+        const int n_own = own.count(), parts = n_own >= 8 ? 4 : (n_own >= 2 ? 2 : 1);
         const size_t layer_bytes = m->layer_texels() * m->s_texel_bytes();
         for (int part = 0; part < parts; ++part) {
-          const pas::LayerSet band{part * r_n / parts, (part + 1) * r_n / parts, 1};
+          const pas::LayerSet band{own.begin + part * n_own / parts, own.begin + (part + 1) * n_own / parts, 1};
           if ((st = run_phase(m, (int)gi, 5, (int)order, blend, main, ds_in, ds_out, 0, &band)) != PAS_OK) return st;
           PAS_CUDA(copy_after(main, PAS_TEXTURE_SCATTERING, (size_t)band.begin * layer_bytes,
                               (size_t)band.count() * layer_bytes));
@@ -1167,6 +1181,7 @@ pas_status pas_model_init_async(pas_model* m, unsigned int num_scattering_orders
       } else if ((st = run_phase(m, (int)gi, 5, (int)order, blend, main, ds_in, ds_out)) != PAS_OK) {
         return st;
       }
+      if (m->peer) m->exchanges += 1;  // the next order uses the other density buffer / xE half
       timer.mark("multiple_scattering_" + tag);
       if ((st = capture_copy(m, "delta_multiple_" + tag, ds_out, m->n_s(), nc, off, true)) != PAS_OK) return st;
       ds_in = ds_out;
@@ -1174,15 +1189,19 @@ pas_status pas_model_init_async(pas_model* m, unsigned int num_scattering_orders
     // the next group restarts with the transmittance pass, which the side stream may still read
     PAS_CUDA(main_after_side());
   }
-  if (pipe_out) {
+  if (pipe_out && lead) {
     if (num_scattering_orders == 1) PAS_CUDA(copy_after(main, PAS_TEXTURE_IRRADIANCE, 0, m->n_e() * 16));
     if (m->num_precomputed_wavelengths > 3 && !fused_rgb) {
       PAS_CUDA(copy_after(main, PAS_TEXTURE_TRANSMITTANCE, 0, m->n_t() * 16));
     }
-    // the main stream ends after the last copy: one synchronisation covers everything
-    PAS_CUDA(cudaEventRecord(m->ev_copy, m->copy));
-    PAS_CUDA(cudaStreamWaitEvent(main, m->ev_copy, 0));
   }
+  auto join_copies = [&]() -> cudaError_t {
+    // the main stream ends after the last copy: one synchronisation covers everything
+    if (!pipe_out) return cudaSuccess;
+    cudaError_t e = cudaEventRecord(m->ev_copy, m->copy);
+    return e != cudaSuccess ? e : cudaStreamWaitEvent(main, m->ev_copy, 0);
+  };
+  if (!(m->world > 1 && m->peer)) PAS_CUDA(join_copies());
   if (m->world > 1 && m->peer) {
     // every rank ends with the complete scattering table(s): push this rank's layers, then barrier
     const pas::LayerSet ks = m->layers();
@@ -1205,6 +1224,9 @@ pas_status pas_model_init_async(pas_model* m, unsigned int num_scattering_orders
       PAS_CUDA(pas::launch_peer_push(m->M.p, layer_bytes, (size_t)ks.begin * layer_bytes, tm, main, ks.count(),
                                      (size_t)ks.stride * layer_bytes));
     }
+    // (host copies of this rank's layers, if any, end before the barrier: passing it means that every
+    // rank's part of the shared host tables is written)
+    PAS_CUDA(join_copies());
     pas_status st = peer_barrier(m, 0, main);
     if (st != PAS_OK) return st;
     m->launches += m->combined ? 1 : 2;

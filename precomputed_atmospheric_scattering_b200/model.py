@@ -98,6 +98,7 @@ def load_library() -> ctypes.CDLL:
         lib.pas_model_init_async.argtypes = [ctypes.c_void_p, ctypes.c_uint]
         lib.pas_model_wait.argtypes = [ctypes.c_void_p]
         lib.pas_model_set_host_outputs.argtypes = [ctypes.c_void_p] + [ctypes.c_void_p] * 4
+        lib.pas_model_set_host_output_mode.argtypes = [ctypes.c_void_p, ctypes.c_int]
         lib.pas_model_texture_info.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(_TextureInfo)]
         lib.pas_model_texture_device_ptr.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]
         lib.pas_model_read_texture.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t]
@@ -303,6 +304,11 @@ class Model:
             ptrs.append(ctypes.c_void_p(arr.ctypes.data))
         self._host_outputs = (transmittance, scattering, single_mie_scattering, irradiance)  # keep alive
         _check(self._lib.pas_model_set_host_outputs(self._h, *ptrs))
+
+    def set_host_output_mode(self, own_layers_only: bool) -> None:
+        """Multi-GPU worlds: copy out only the layers this rank computed (the registered arrays are then
+        host tables SHARED by the ranks, world.shared_host_tables) -- pas_model_set_host_output_mode."""
+        _check(self._lib.pas_model_set_host_output_mode(self._h, 1 if own_layers_only else 0))
 
     def GetShaderSource(self, glsl_directory: str) -> str:
         """The source atmosphere::Model::shader() compiles (atmosphere/model.cc:691-744, 769-772)."""

@@ -222,3 +222,60 @@ def sum_over_ranks(value: float, group=None) -> float:
     t = torch.tensor([float(value)], dtype=torch.float64, device=_host_device(group))
     dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
     return float(t.item())
+
+
+class SharedHostTables:
+    """One set of host product tables for all the ranks of a box: POSIX shared memory (/dev/shm) mapped
+    by every rank and page-locked for CUDA by each of them (cudaHostRegister), so that every rank can
+    copy the layers it computed straight into the common tables (Model.set_host_output_mode(True)).
+    ``arrays[which]`` are numpy views shaped like the model's tables."""
+
+    def __init__(self, model, which, group=None, tag: str = "tables"):
+        import numpy as np
+        rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.arrays, self._maps, self._registered, self._paths = {}, [], [], []
+        # a name every rank derives alike and that other jobs on the box do not share
+        job = os.environ.get("MASTER_PORT", "0") + "_" + os.environ.get("TORCHELASTIC_RUN_ID", str(os.getppid()))
+        for w in which:
+            info = model.texture_info(w)
+            shape = ((info.depth,) if info.depth > 1 else ()) + (info.height, info.width, 4)
+            dtype = np.float16 if info.bytes_per_channel == 2 else np.float32
+            nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+            path = f"/dev/shm/pas_b200_{job}_{tag}_{w}"
+            if rank == 0:
+                with open(path, "wb") as f:
+                    f.truncate(nbytes)
+            self._paths.append(path)
+            self.arrays[w] = (path, shape, dtype, nbytes)
+        if dist.is_initialized():
+            dist.barrier(group)
+        cudart = torch.cuda.cudart()
+        for w, (path, shape, dtype, nbytes) in list(self.arrays.items()):
+            a = np.memmap(path, dtype=dtype, mode="r+", shape=shape)
+            err = cudart.cudaHostRegister(a.ctypes.data, nbytes, 0)
+            if int(err) != 0:
+                raise RuntimeError(f"cudaHostRegister({path}) failed: {err}")
+            self._maps.append(a)
+            self._registered.append(a.ctypes.data)
+            self.arrays[w] = a
+        self._rank, self._group = rank, group
+
+    def close(self):
+        cudart = torch.cuda.cudart()
+        for p in self._registered:
+            cudart.cudaHostUnregister(p)
+        self._registered = []
+        self.arrays, self._maps = {}, []
+        if dist.is_initialized():
+            dist.barrier(self._group)
+        if self._rank == 0:
+            for path in self._paths:
+                try:
+                    os.unlink(path)
+                except OSError:
+                    pass
+
+
+def shared_host_tables(model, which, group=None, tag: str = "tables") -> SharedHostTables:
+    """COLLECTIVE: host tables shared by the ranks (see SharedHostTables)."""
+    return SharedHostTables(model, which, group, tag)

@@ -105,6 +105,35 @@ def _variant_worker(rank, world_size, port, out_dir, exchange):
                 out["M"] = model.single_mie_scattering
             np.savez(os.path.join(out_dir, f"{name}_rank{rank}.npz"), **out)
             model.close()
+        # shared host tables: every rank copies only the layers it computed into ONE set of host tables
+        # (POSIX shared memory, page-locked by every rank); when Init returns on a rank, all of it is there
+        for spec, kw in ((pas.small_planet(), dict(sizes=SIZES)), (pas.earth(15, half_precision=True), {})):
+            m = pas.Model.from_spec(spec, device=rank, **kw)
+            world.attach(m, exchange=exchange)
+            which = [pas.TEXTURE_TRANSMITTANCE, pas.TEXTURE_SCATTERING, pas.TEXTURE_IRRADIANCE]
+            shared = world.shared_host_tables(m, which, tag=f"test{len(kw)}")
+            m.set_host_outputs(transmittance=shared.arrays[pas.TEXTURE_TRANSMITTANCE],
+                               scattering=shared.arrays[pas.TEXTURE_SCATTERING],
+                               irradiance=shared.arrays[pas.TEXTURE_IRRADIANCE])
+            m.set_host_output_mode(True)
+            plain = pas.Model.from_spec(spec, device=rank, **kw)     # every rank copies everything, after Init
+            world.attach(plain, exchange=exchange)
+            plain.Init(4)
+            want = {w: plain.texture(w, as_float32=False) for w in which}
+            plain.close()
+            for attempt in range(2):
+                dist.barrier()
+                if rank == 0:
+                    for a in shared.arrays.values():
+                        a[...] = 0
+                dist.barrier()
+                m.Init(4)
+                for w in which:
+                    assert np.array_equal(shared.arrays[w], m.texture(w, as_float32=False)), (w, attempt, rank)
+                    assert np.array_equal(shared.arrays[w], want[w]), (w, attempt, rank)
+            m.set_host_outputs()
+            shared.close()
+            m.close()
         # one barrier sequence per peer world: a second model of the world cannot start its Init while
         # the first is in flight (its barriers would release the first model's early); once the first
         # has been waited for, it runs and gives the same tables
