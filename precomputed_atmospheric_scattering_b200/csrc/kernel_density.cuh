@@ -651,9 +651,11 @@ cudaError_t launch_one(const PasGeometry& g, int nc, const PasDensityDir* dirs, 
                        const float* cR, const float* cM, const float* tabA, const float* tabB,
                        const float* dE, float* dJ, const PeerTables& mirrors, LayerSet layers,
                        cudaStream_t stream) {
-  const int threads = 256;
   const int texels = g.sz.mu_n * g.sz.nu_n;
   if (layers.count() == 0) return cudaSuccess;
+  // (half-size blocks for the small grids of an 8-GPU world -- 1024 blocks of 128 threads instead of 512
+  // of 256 on 148 SMs -- were measured: no difference, 0.1356 vs 0.1345 ms)
+  const int threads = 256;
   dim3 grid((texels + threads - 1) / threads, g.sz.mu_s_n, layers.count());
   constexpr int Q = CP / 4;
   // irradiance row + differences, then (MIRROR) the output staging [256][Q + 1] float4

@@ -19,7 +19,8 @@ __device__ __forceinline__ double warp_sum(double v) {
 __global__ void __launch_bounds__(256)
 transmittance_kernel(const __grid_constant__ PasGeometry g, const __grid_constant__ PasSpectrum s,
                      float* __restrict__ T, const __grid_constant__ PeerTables mirrors, int j_begin,
-                     int j_end, const __grid_constant__ RgbExtinction rgb, float* __restrict__ rgba) {
+                     int j_end, const __grid_constant__ RgbExtinction rgb, float* __restrict__ rgba,
+                     const __grid_constant__ PeerTables rgba_mirrors) {
   const int texel = j_begin * g.sz.t_w + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
   const int lane = threadIdx.x & 31;
   if (texel >= j_end * g.sz.t_w) return;
@@ -66,6 +67,7 @@ transmittance_kernel(const __grid_constant__ PasGeometry g, const __grid_constan
       t = (float)exp(-(rgb.beta_r[c] * acc[0] + rgb.beta_m_ext[c] * acc[1] + rgb.beta_abs[c] * acc[2]));
     }
     rgba[(size_t)texel * 4 + c] = t;
+    for (int p = 0; p < rgba_mirrors.n; ++p) rgba_mirrors.tab[p][(size_t)texel * 4 + c] = t;
   }
 }
 
@@ -214,18 +216,30 @@ cudaError_t launch_transmittance(const PasGeometry& g, const PasSpectrum& s, flo
   const int n = g.sz.t_w * g.sz.t_h;
   const int warps_per_block = 8;
   transmittance_kernel<<<(n + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0,
-                         stream>>>(g, s, T, PeerTables{}, 0, g.sz.t_h, e, rgba);
+                         stream>>>(g, s, T, PeerTables{}, 0, g.sz.t_h, e, rgba, PeerTables{});
   return cudaGetLastError();
 }
 
 cudaError_t launch_transmittance_rows(const PasGeometry& g, const PasSpectrum& s, float* T,
                                       const PeerTables& mirrors, int j_begin, int j_end,
-                                      cudaStream_t stream) {
+                                      cudaStream_t stream, const PasSpectrum* rgb, float* rgba,
+                                      const PeerTables* rgba_mirrors) {
   const int n = g.sz.t_w * (j_end - j_begin);
   if (n <= 0) return cudaSuccess;
+  RgbExtinction e{};
+  if (rgb != nullptr && rgba != nullptr) {
+    for (int c = 0; c < 3; ++c) {
+      e.beta_r[c] = rgb->beta_r[c];
+      e.beta_m_ext[c] = rgb->beta_m_ext[c];
+      e.beta_abs[c] = rgb->beta_abs[c];
+    }
+  } else {
+    rgba = nullptr;
+  }
   const int warps_per_block = 8;
   transmittance_kernel<<<(n + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0,
-                         stream>>>(g, s, T, mirrors, j_begin, j_end, RgbExtinction{}, nullptr);
+                         stream>>>(g, s, T, mirrors, j_begin, j_end, e, rgba,
+                                   rgba != nullptr && rgba_mirrors != nullptr ? *rgba_mirrors : PeerTables{});
   return cudaGetLastError();
 }
 

@@ -51,10 +51,12 @@ struct RgbExtinction {
 cudaError_t launch_transmittance(const PasGeometry& g, const PasSpectrum& s, float* T,
                                  cudaStream_t stream, const PasSpectrum* rgb = nullptr,
                                  float* rgba = nullptr);
-// Rows [j_begin, j_end) only, stored to T and to its mirrors (multi-GPU: one band of rows per rank).
+// Rows [j_begin, j_end) only, stored to T and to its mirrors (multi-GPU: one band of rows per rank);
+// optionally the same rows of the final RGBA table, to `rgba` and its mirrors.
 cudaError_t launch_transmittance_rows(const PasGeometry& g, const PasSpectrum& s, float* T,
                                       const PeerTables& mirrors, int j_begin, int j_end,
-                                      cudaStream_t stream);
+                                      cudaStream_t stream, const PasSpectrum* rgb = nullptr,
+                                      float* rgba = nullptr, const PeerTables* rgba_mirrors = nullptr);
 // Packs channels 0..2 of an interleaved transmittance table into the RGBA32F product table.
 cudaError_t launch_pack_rgba(const float* table, int n_texels, int nc, float* rgba,
                              cudaStream_t stream);

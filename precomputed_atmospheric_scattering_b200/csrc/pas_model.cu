@@ -364,7 +364,7 @@ struct pas_model {
   bool symm = false;
   char* arena[PAS_MAX_PEERS + 1] = {};
   char* arena_mc = nullptr;        // multicast address of the arenas, or nullptr
-  size_t off_T = 0, off_dJ[2] = {0, 0}, off_xE = 0, off_Sx = 0, off_Mx = 0;
+  size_t off_T = 0, off_dJ[2] = {0, 0}, off_xE = 0, off_Sx = 0, off_Mx = 0, off_Tx = 0;
   // destinations of this rank's stores for an exchanged table at arena offset `off`: the one multicast
   // address when there is one (it includes the local copy), else the table in every other rank's arena
   pas::PeerTables mirrors_at(size_t off) const {
@@ -410,6 +410,10 @@ struct pas_model {
   // slower than slabs on 4 and 8 B200 (2.34 vs 2.31 ms, 1.69 vs 1.54 ms).
   pas::LayerSet layers() const {
     if (world == 1) return pas::LayerSet{0, geom.sz.r_n, 1};
+    // PAS_LAYER_DEAL=rr (peer / symmetric worlds): rank r takes layers r, r + world, ... -- the density
+    // pass costs more at high altitude (wider ground windows), dealing the layers evens the ranks out
+    static const bool deal = getenv("PAS_LAYER_DEAL") != nullptr && std::string(getenv("PAS_LAYER_DEAL")) == "rr";
+    if (deal && peer) return pas::LayerSet{rank, geom.sz.r_n, world};
     const int base = geom.sz.r_n / world, extra = geom.sz.r_n % world;
     const int k_begin = rank * base + std::min(rank, extra);
     return pas::LayerSet{k_begin, k_begin + base + (rank < extra ? 1 : 0), 1};
@@ -698,9 +702,22 @@ pas_status run_phase(pas_model* m, int gi, int phase, int order, bool accumulate
           pas_status st = peer_barrier(m, channel, stream);
           if (st != PAS_OK) return st;
         }
-        PAS_CUDA(pas::launch_transmittance_rows(g, sp, m->T.f(), mirrors, j0, j1, stream));
+        if (m->fuse_rgb_transmittance && gi == 0) {
+          // symmetric worlds: the same launch fills this rank's rows of the final RGBA table, in the
+          // staging area of every rank's arena; copied into the model's own table after the barrier
+          const pas::PeerTables rgba_mirrors = m->mirrors_at(m->off_Tx);
+          PAS_CUDA(pas::launch_transmittance_rows(g, sp, m->T.f(), mirrors, j0, j1, stream, &m->rgb_spectrum,
+                                                  reinterpret_cast<float*>(m->arena[m->rank] + m->off_Tx),
+                                                  &rgba_mirrors));
+        } else {
+          PAS_CUDA(pas::launch_transmittance_rows(g, sp, m->T.f(), mirrors, j0, j1, stream));
+        }
         pas_status st = peer_barrier(m, channel, stream);
         if (st != PAS_OK) return st;
+        if (m->fuse_rgb_transmittance && gi == 0) {
+          PAS_CUDA(cudaMemcpyAsync(m->T_rgba.p, m->arena[m->rank] + m->off_Tx, m->n_t() * 16,
+                                   cudaMemcpyDeviceToDevice, stream));
+        }
       } else if (m->fuse_rgb_transmittance && gi == 0) {
         PAS_CUDA(pas::launch_transmittance(g, sp, m->T.f(), stream, &m->rgb_spectrum, m->T_rgba.f()));
       } else {
@@ -1099,12 +1116,33 @@ pas_status pas_model_init_async(pas_model* m, unsigned int num_scattering_orders
     }
     return e;
   };
+  // layers `ls` of a 3-D product table (a strided set when the layers are dealt round-robin)
+  auto copy_layers_after = [&](cudaStream_t producer, int which, const pas::LayerSet& ls) -> cudaError_t {
+    if (m->host_out[which] == nullptr || ls.count() == 0) return cudaSuccess;
+    const size_t layer_bytes = m->layer_texels() * m->s_texel_bytes();
+    if (ls.stride == 1) return copy_after(producer, which, (size_t)ls.begin * layer_bytes, (size_t)ls.count() * layer_bytes);
+    const DeviceBuffer* buf = nullptr;
+    pas_texture_info info;
+    if (texture_lookup(m, (pas_texture)which, &buf, &info) != PAS_OK || !info.present) return cudaSuccess;
+    cudaError_t e = cudaEventRecord(m->ev_copy, producer);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(m->copy, m->ev_copy, 0);
+    if (e == cudaSuccess) {
+      const size_t off = (size_t)ls.begin * layer_bytes, pitch = (size_t)ls.stride * layer_bytes;
+      e = cudaMemcpy2DAsync(static_cast<char*>(m->host_out[which]) + off, pitch, static_cast<const char*>(buf->p) + off,
+                            pitch, layer_bytes, (size_t)ls.count(), cudaMemcpyDeviceToHost, m->copy);
+    }
+    return e;
+  };
+  // elements [a, b) of a layer set
+  auto sub_set = [](const pas::LayerSet& ls, int a, int b) {
+    return pas::LayerSet{ls.begin + a * ls.stride, std::min(ls.end, ls.begin + b * ls.stride), ls.stride};
+  };
   PhaseTimer timer(m);
   timer.mark("start");
   // final transmittance at 680/550/440 nm (model.cc:951-963). One GPU: filled by the transmittance
   // launch of the first channel group (same optical lengths). Peer worlds compute the transmittance
   // in bands of rows, so there the RGB table is a launch of its own, beside everything else.
-  const bool fused_rgb = m->num_precomputed_wavelengths > 3 && !m->peer;
+  const bool fused_rgb = m->num_precomputed_wavelengths > 3 && (!m->peer || m->symm);
   if (m->num_precomputed_wavelengths > 3 && !fused_rgb) {
     PAS_CUDA(side_after_main());
     PAS_CUDA(pas::launch_transmittance(m->geom, m->rgb_spectrum, m->T_rgb.f(), side));
@@ -1135,12 +1173,8 @@ pas_status pas_model_init_async(pas_model* m, unsigned int num_scattering_orders
     const bool last_group = gi + 1 == m->groups.size();
     if (pipe_out && last_group) {
       // the single-Mie table is written by single scattering only (model.cc:151-156)
-      const size_t layer_bytes = m->layer_texels() * m->s_texel_bytes();
-      PAS_CUDA(copy_after(main, PAS_TEXTURE_SINGLE_MIE, (size_t)own.begin * layer_bytes, (size_t)own.count() * layer_bytes));
-      if (num_scattering_orders == 1) {
-        PAS_CUDA(copy_after(main, PAS_TEXTURE_SCATTERING, (size_t)own.begin * layer_bytes,
-                            (size_t)own.count() * layer_bytes));
-      }
+      PAS_CUDA(copy_layers_after(main, PAS_TEXTURE_SINGLE_MIE, own));
+      if (num_scattering_orders == 1) PAS_CUDA(copy_layers_after(main, PAS_TEXTURE_SCATTERING, own));
     }
     timer.mark("single_scattering");
     if ((st = capture_copy(m, "delta_rayleigh", m->dR.f(), m->n_s(), nc, off, true)) != PAS_OK) return st;
@@ -1171,12 +1205,10 @@ pas_status pas_model_init_async(pas_model* m, unsigned int num_scattering_orders
         // E is final (side stream); S becomes final band by band
         if (lead) PAS_CUDA(copy_after(side, PAS_TEXTURE_IRRADIANCE, 0, m->n_e() * 16));
         const int n_own = own.count(), parts = n_own >= 8 ? 4 : (n_own >= 2 ? 2 : 1);
-        const size_t layer_bytes = m->layer_texels() * m->s_texel_bytes();
         for (int part = 0; part < parts; ++part) {
-          const pas::LayerSet band{own.begin + part * n_own / parts, own.begin + (part + 1) * n_own / parts, 1};
+          const pas::LayerSet band = sub_set(own, part * n_own / parts, (part + 1) * n_own / parts);
           if ((st = run_phase(m, (int)gi, 5, (int)order, blend, main, ds_in, ds_out, 0, &band)) != PAS_OK) return st;
-          PAS_CUDA(copy_after(main, PAS_TEXTURE_SCATTERING, (size_t)band.begin * layer_bytes,
-                              (size_t)band.count() * layer_bytes));
+          PAS_CUDA(copy_layers_after(main, PAS_TEXTURE_SCATTERING, band));
         }
       } else if ((st = run_phase(m, (int)gi, 5, (int)order, blend, main, ds_in, ds_out)) != PAS_OK) {
         return st;
@@ -1237,6 +1269,17 @@ pas_status pas_model_init_async(pas_model* m, unsigned int num_scattering_orders
       auto gather = [&](void* table, size_t off) -> cudaError_t {
         const char* src = m->arena[m->rank] + off;
         cudaError_t e = cudaSuccess;
+        if (ks.stride > 1) {
+          // dealt layers: the layers of rank r are r, r + world, ...
+          const size_t pitch = (size_t)ks.stride * layer_bytes;
+          for (int r = 0; r < m->world && e == cudaSuccess; ++r) {
+            if (r == m->rank) continue;
+            const int n = (m->geom.sz.r_n - r + m->world - 1) / m->world;
+            e = cudaMemcpy2DAsync(static_cast<char*>(table) + (size_t)r * layer_bytes, pitch, src + (size_t)r * layer_bytes,
+                                  pitch, layer_bytes, (size_t)n, cudaMemcpyDeviceToDevice, main);
+          }
+          return e;
+        }
         if (lo > 0) e = cudaMemcpyAsync(table, src, lo, cudaMemcpyDeviceToDevice, main);
         if (e == cudaSuccess && hi < all) {
           e = cudaMemcpyAsync(static_cast<char*>(table) + hi, src + hi, all - hi, cudaMemcpyDeviceToDevice, main);
@@ -1696,7 +1739,7 @@ namespace {
 // Layout of a model's exchange tables inside a symmetric arena: flag words first (fixed place, whatever
 // the model), then the tables, each aligned to 1 KiB.
 struct ArenaLayout {
-  size_t flags = 0, T = 0, dJ[2] = {0, 0}, xE = 0, Sx = 0, Mx = 0, bytes = 0;
+  size_t flags = 0, T = 0, dJ[2] = {0, 0}, xE = 0, Sx = 0, Mx = 0, Tx = 0, bytes = 0;
 };
 ArenaLayout arena_layout(const pas_model* m, int world) {
   ArenaLayout a;
@@ -1713,6 +1756,7 @@ ArenaLayout arena_layout(const pas_model* m, int world) {
   a.xE = take((size_t)2 * world * m->xe_stride() * sizeof(float));
   a.Sx = take(m->n_s() * m->s_texel_bytes());
   a.Mx = m->combined ? a.Sx : take(m->n_s() * m->s_texel_bytes());
+  a.Tx = take(m->n_t() * 16);   // staging of the final RGBA transmittance (rows computed by different ranks)
   a.bytes = at;
   return a;
 }
@@ -1777,6 +1821,7 @@ pas_status pas_model_attach_symmetric(pas_model* m, int rank, int world_size, vo
   m->off_xE = a.xE;
   m->off_Sx = a.Sx;
   m->off_Mx = a.Mx;
+  m->off_Tx = a.Tx;
   const size_t cp = PAS_CHANNEL_PITCH(m->max_nc());
   char* mine = m->arena[rank];
   m->T.adopt(mine + a.T, m->n_t() * cp * sizeof(float));
