@@ -72,10 +72,10 @@ CONFIGS = {
                      "dimension: T 1024x256, E 64x16, S 1024x512x128 ((nu, mu_s) = (8, 128)), combined "
                      "textures, fp32 final tables"),
     5: dict(wavelengths=3, orders=4, half=True, sizes=None,
-            metric="ensemble_64_atmospheres_precompute_and_1080p_render_ms",
+            metric="ensemble_64_atmospheres_precompute_and_1080p_sky_radiance_ms",
             workload="64 earth atmospheres (4 turbidity x 4 ozone x 4 albedo, seeded sweep), RGB, 4 scattering "
-                     f"orders each, {SIZES_TEXT}, 16 precomputations in flight, then one 1920x1080 render of "
-                     "the model_test scene per atmosphere"),
+                     f"orders each, {SIZES_TEXT}, 16 precomputations in flight, then one 1920x1080 GetSkyRadiance "
+                     "image per atmosphere"),
 }
 
 
@@ -554,27 +554,46 @@ def run_b200(args, rank, world_size, local_rank):
 
 
 def run_ensemble(args, rank, world_size, local_rank, barrier):
-    """BASELINE config 5: 64 atmospheres precomputed with 16 in flight (pas_model_init_async), then one
-    1920x1080 render of the model_test scene per atmosphere. Multi-GPU: the atmospheres are dealt
-    round-robin to the ranks (independent models, no exchange) -- weak in nothing, strong scaling."""
+    """BASELINE config 5: 64 atmospheres precomputed with 16 in flight (pas_model_init_async), then, per
+    atmosphere, one 1920x1080 image of sky radiance through the product's render-time lookup
+    (pas_model_get_sky_radiance = GetSkyRadiance of functions.glsl:1705-1769, one query per pixel, view
+    rays of the reference's test camera, inputs and outputs resident on the device). Multi-GPU: the
+    atmospheres are dealt round-robin to the ranks (independent models, no exchange)."""
     import numpy as np
+    import torch
     import precomputed_atmospheric_scattering_b200 as pas
-    from precomputed_atmospheric_scattering_b200 import ensemble, scene, world
+    from precomputed_atmospheric_scattering_b200 import ensemble, world
+    from tests import scene
     cfg = CONFIGS[5]
     specs = ensemble.sweep(num_precomputed_wavelengths=3, half_precision=True)[rank::world_size]
-    view = scene.model_test_view(65.0, 90.0, False, width=1920, height=1080,
-                                 sun_angular_radius=specs[0].sun_angular_radius)
+    W, H = 1920, 1080
+    view = scene.model_test_view(65.0, 90.0, False, width=W, height=H, sun_angular_radius=specs[0].sun_angular_radius)
+    # view rays of every pixel (reference/model_test.cc:690-711), camera relative to the planet centre
+    M = np.asarray(view.model_from_clip, dtype=np.float64).reshape(3, 3)
+    x = 2.0 * (np.arange(W) + 0.5) / W - 1.0
+    y = 1.0 - 2.0 * (np.arange(H) + 0.5) / H
+    rays = np.stack(np.broadcast_arrays(x[None, :], y[:, None], 1.0), axis=-1) @ M.T
+    rays /= np.linalg.norm(rays, axis=-1, keepdims=True)
+    dev = torch.device("cuda", local_rank)
+    n = W * H
+    d_rays = torch.from_numpy(rays.reshape(n, 3)).to(dev)
+    d_cam = (torch.tensor(view.camera, dtype=torch.float64) - torch.tensor(view.earth_center, dtype=torch.float64)).to(dev).repeat(n, 1)
+    d_sun = torch.tensor(view.sun_direction, dtype=torch.float64, device=dev).repeat(n, 1)
+    d_L = torch.empty((n, 3), dtype=torch.float32, device=dev)
+    d_T = torch.empty((n, 3), dtype=torch.float32, device=dev)
+    host_image = torch.empty((n, 3), dtype=torch.float32).pin_memory()
 
     def step():
         t0 = time.perf_counter()
         models = ensemble.precompute(specs, cfg["orders"], device=local_rank, max_in_flight=16)
-        import torch
         torch.cuda.synchronize()
         t1 = time.perf_counter()
         render_ms = 0.0
         for m in models:
-            m.render_scene(view, want_argb=True)
+            m.sky_radiance_device(n, d_cam.data_ptr(), d_rays.data_ptr(), 0, d_sun.data_ptr(), d_L.data_ptr(), d_T.data_ptr())
             render_ms += m.last_render_ms()
+            host_image.copy_(d_L)       # every image goes back to the host
+        torch.cuda.synchronize()
         t2 = time.perf_counter()
         launches = sum(m.last_launch_count() + 1 for m in models)
         for m in models:
@@ -589,13 +608,14 @@ def run_ensemble(args, rank, world_size, local_rank, barrier):
     pre, ren, dev_ren, launches = [], [], [], 0
     steps = max(1, min(args.steps, 5))
     for _ in range(steps):
-        a, b, c, n = step()
+        a, b, c, nl = step()
         pre.append(a), ren.append(b), dev_ren.append(c)
-        launches += n
+        launches += nl
     barrier()
     clocks = sampler.finish()
     pre_ms = world.max_over_ranks(sum(pre) / steps)
     ren_ms = world.max_over_ranks(sum(ren) / steps)
+    finite = bool(torch.isfinite(host_image).all() and (host_image >= 0).all() and host_image.max() > 0)
     if rank != 0:
         return 0
     total = pre_ms + ren_ms
@@ -608,10 +628,11 @@ def run_ensemble(args, rank, world_size, local_rank, barrier):
         "render_ms_64_x_1080p_wall_with_readback": round(ren_ms, 3),
         "render_kernel_ms_per_1080p_image": round(sum(dev_ren) / steps / len(specs), 4),
         "e2e": {"value": round(total, 3), "unit": "ms", "h2d_bytes_per_step": 64 * 3368,
-                "d2h_bytes_per_step": 64 * (1920 * 1080 * 16),
-                "what": "host wall clock: 64 x Model(host arrays) + InitAsync/Wait, then 64 renders read back to host (rgb fp32 + argb)"},
-        "gpu_launches": launches, "clocks": clocks, "parity": None,
-        "parity_note": "tests/test_gpu_configs.py checks this batch against blocking Init, the oracle and the oracle renderer",
+                "d2h_bytes_per_step": 64 * n * 12,
+                "what": "host wall clock: 64 x Model(host arrays) + InitAsync/Wait, then 64 x 1080p GetSkyRadiance images read back to pinned host memory"},
+        "gpu_launches": launches, "clocks": clocks, "parity": None, "images_finite": finite,
+        "parity_note": "tests/test_gpu_configs.py checks this batch against blocking Init and the oracle, and renders of the "
+                       "reference's test scene with these tables against the oracle renderer",
     }))
     return 0
 

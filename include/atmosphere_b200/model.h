@@ -99,6 +99,10 @@ class Model {
     p.combine_scattering_textures = combine_scattering_textures ? 1 : 0;
     p.half_precision = half_precision ? 1 : 0;
     Check(pas_model_create(&p, &model_));
+#ifdef PAS_WITH_GL
+    // like the reference (model.cc:769-776) the shader is compiled here: shader() is valid before Init
+    CompileShader();
+#endif
   }
 
   Model(const Model&) = delete;             // owns device memory and GL objects
@@ -117,7 +121,6 @@ class Model {
     Check(pas_model_init(model_, num_scattering_orders));
 #ifdef PAS_WITH_GL
     UploadTextures();
-    if (atmosphere_shader_ == 0) CompileShader();
 #endif
   }
 
@@ -182,6 +185,12 @@ class Model {
     return texels;
   }
   void SaveDat(const std::string& directory) const { Check(pas_model_save_dat(model_, directory.c_str())); }
+  // demo/webgl/precompute.cc:81-106: the .dat files + atmosphere_shader.txt + the caller's own shaders
+  void SaveWebGl(const std::string& directory, const std::string& vertex_shader,
+                 const std::string& fragment_shader) const {
+    Check(pas_model_save_webgl(model_, directory.c_str(), glsl_directory_.c_str(), vertex_shader.c_str(),
+                               fragment_shader.c_str()));
+  }
   pas_model* handle() const { return model_; }
 
  private:

@@ -184,31 +184,14 @@ pas_status pas_model_get_sun_and_sky_irradiance(pas_model* model, int use_lumina
                                                 const double* sun_direction, float* sun_irradiance,
                                                 float* sky_irradiance);
 
-/* The uniforms of the reference's integration-test scene shader: a sphere on a spherical planet
- * with shadows and light shafts (atmosphere/reference/model_test.glsl; uniforms
- * reference/model_test.cc:127-134, values :310-318, 436-477). Lengths in the model's length unit. */
-typedef struct pas_scene_view {
-  double camera[3];
-  double earth_center[3];
-  double sun_direction[3];
-  double sun_size[2];          /* tan and cos of the sun's angular radius */
-  double sphere_center[3];
-  double sphere_radius;
-  double model_from_clip[9];   /* row major: view ray = M * (x, y, 1), clip x, y in [-1, 1] */
-  double ground_albedo[3];     /* at 680 / 550 / 440 nm */
-  double sphere_albedo[3];
-  double exposure;
-  int use_luminance;
-  int width, height;
-} pas_scene_view;
-
-/* Renders GetViewRayRadiance (model_test.glsl:218-348) for every pixel, pixel (0, 0) at the top left
- * with the view rays of model_test.cc:688-711. rgb (width*height*3 floats, radiance or luminance
- * before tone mapping) and argb (width*height words, tone-mapped with
- * pow(1 - exp(-c * exposure), 1/2.2) and truncated like RenderCpuImage, model_test.cc:726-736) may
- * each be NULL; host or device pointers. */
-pas_status pas_model_render_scene(pas_model* model, const pas_scene_view* view, float* rgb,
-                                  uint32_t* argb);
+/* For CUDA renderers that call the lookups from their own kernels: fills `out` with the
+ * pas::RenderContext of csrc/kernel_render.cuh (geometry, device pointers of the four product tables,
+ * the constants at 680/550/440 nm, luminance factors or 1) -- the CUDA counterpart of the reference
+ * handing its users GLSL source + sampler uniforms (atmosphere/model.cc:221-281, 984-1011). The context
+ * is valid until the next pas_model_init / destroy of the model. Call with out == NULL to get the size.
+ * (The reference's integration-test scene, reference/model_test.glsl, is rendered this way by the tests:
+ * tests/cuda/scene_kernel.cu. It is test infrastructure, not part of this library.) */
+pas_status pas_model_render_context(pas_model* model, int use_luminance, void* out, size_t* bytes);
 /* Device time of the last render / lookup kernel in milliseconds (CUDA events on the model's
  * stream, copies excluded). */
 pas_status pas_model_last_render_ms(const pas_model* model, float* ms);
@@ -220,6 +203,17 @@ pas_status pas_model_last_render_ms(const pas_model* model, float* ms);
  * get the required size (including the terminating NUL) in *size. */
 pas_status pas_model_shader_source(const pas_model* model, const char* glsl_directory,
                                    char* buffer, size_t* size);
+/* The same source from the constructor parameters alone -- no model, no device: the shader depends on
+ * the parameters only, which is why the reference compiles it in its constructor, before Init
+ * (atmosphere/model.cc:769-776). */
+pas_status pas_shader_source(const pas_model_params* params, const char* glsl_directory, char* buffer,
+                             size_t* size);
+/* The hand-off of atmosphere/demo/webgl/precompute.cc:50-61, 81-106 to the WebGL viewer: the .dat
+ * files of pas_model_save_dat plus atmosphere_shader.txt (= pas_model_shader_source) and, when the caller
+ * passes them, vertex_shader.txt / fragment_shader.txt (the demo's own shaders: they belong to the
+ * caller, demo/demo.cc:75-97 and demo/demo.glsl; NULL = not written). */
+pas_status pas_model_save_webgl(pas_model* model, const char* directory, const char* glsl_directory,
+                                const char* vertex_shader_source, const char* fragment_shader_source);
 
 /* The SKY/SUN_SPECTRAL_RADIANCE_TO_LUMINANCE constants baked into that shader
  * (atmosphere/model.cc:562-595, 668-686). out6 = sky rgb, sun rgb. */

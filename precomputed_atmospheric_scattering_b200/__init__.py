@@ -7,13 +7,13 @@ atmosphere definitions of the bench configs.
 """
 from .atmospheres import (AtmosphereSpec, ChannelParams, DensityProfileLayer, channel_params, earth,
                           model_test_earth, precomputed_wavelengths, small_planet)
-from . import ensemble, scene
+from . import ensemble
 from .model import (LIB_PATH, Model, PasError, TEXTURE_IRRADIANCE, TEXTURE_SCATTERING,
                     TEXTURE_SINGLE_MIE, TEXTURE_TRANSMITTANCE, convert_spectrum_to_linear_srgb,
                     load_library, measure_device_peaks, nccl_unique_id, release_cached_memory,
-                    spectral_channels, world_is_cached)
+                    shader_source, spectral_channels, world_is_cached)
 
 __all__ = ["AtmosphereSpec", "ChannelParams", "DensityProfileLayer", "Model", "PasError", "LIB_PATH",
-           "channel_params", "earth", "small_planet", "model_test_earth", "scene", "ensemble", "precomputed_wavelengths", "load_library",
-           "nccl_unique_id", "spectral_channels", "measure_device_peaks", "release_cached_memory", "world_is_cached", "convert_spectrum_to_linear_srgb", "TEXTURE_TRANSMITTANCE",
+           "channel_params", "earth", "small_planet", "model_test_earth", "ensemble", "precomputed_wavelengths", "load_library",
+           "nccl_unique_id", "shader_source", "spectral_channels", "measure_device_peaks", "release_cached_memory", "world_is_cached", "convert_spectrum_to_linear_srgb", "TEXTURE_TRANSMITTANCE",
            "TEXTURE_SCATTERING", "TEXTURE_IRRADIANCE", "TEXTURE_SINGLE_MIE"]

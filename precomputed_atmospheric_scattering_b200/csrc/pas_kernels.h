@@ -140,7 +140,7 @@ cudaError_t launch_peer_push(const void* src, size_t bytes, size_t offset_bytes,
 cudaError_t launch_sum_partials(const float* parts, int world, size_t stride, int n, float* out,
                                 cudaStream_t stream);
 
-// ---- render-time use of the tables (kernel_render.cu) -------------------------------------------
+// ---- render-time use of the tables (kernel_render.cuh: device functions; kernel_render.cu: batches) ---
 struct RenderTables {
   const float4* transmittance;  // RGBA32F [t_h][t_w]
   const void* scattering;       // RGBA [r][mu][nu * mu_s], fp32 or fp16
@@ -152,18 +152,6 @@ struct RenderConstants {         // the ATMOSPHERE constants the render function
   double solar[3], rayleigh[3], mie_sca[3];
   double sky_k[3], sun_k[3];     // SKY / SUN_SPECTRAL_RADIANCE_TO_LUMINANCE, or 1 (radiance mode)
 };
-struct RenderView {              // uniforms of reference/model_test.cc:127-134 + image size
-  double camera[3], earth_center[3], sun_direction[3], sun_size[2];
-  double sphere_center[3], sphere_radius;
-  double model_from_clip[9];
-  double ground_albedo[3], sphere_albedo[3];
-  double exposure;
-  int width, height;
-};
-// Test scene of reference/model_test.glsl, one thread per pixel; rgb ([h][w][3] fp32, before tone
-// mapping) and argb ([h][w] tone-mapped words, model_test.cc:726-736) may each be nullptr.
-cudaError_t launch_render_scene(const PasGeometry& g, const RenderTables& t, const RenderConstants& c,
-                                const RenderView& view, float* rgb, unsigned* argb, cudaStream_t stream);
 // GetSkyRadiance (to_point = false: target = view ray) / GetSkyRadianceToPoint (target = point) for
 // n queries; device pointers, vectors [n][3]; shadow_length and transmittance may be nullptr.
 cudaError_t launch_sky_radiance(const PasGeometry& g, const RenderTables& t, const RenderConstants& c,

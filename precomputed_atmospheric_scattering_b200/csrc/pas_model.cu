@@ -26,6 +26,7 @@
 
 #include "../../include/pas_b200.h"
 #include "cie1931.h"
+#include "kernel_render.cuh"
 #include "pas_kernels.h"
 #include "pas_physics.cuh"
 
@@ -839,9 +840,12 @@ extern "C" {
 const char* pas_last_error(void) { return g_last_error.c_str(); }
 int pas_abi_version(void) { return PAS_B200_ABI_VERSION; }
 
-pas_status pas_model_create(const pas_model_params* p, pas_model** out) {
-  if (out == nullptr) return fail(PAS_ERR_INVALID_ARGUMENT, "out_model is NULL");
-  *out = nullptr;
+}  // extern "C"
+
+namespace {
+// The host half of atmosphere::Model::Model (model.cc:613-690): parameters, units, channel grid,
+// luminance matrices and factors. Needs no device: the GLSL source of a model is a function of this alone.
+pas_status build_host_model(const pas_model_params* p, std::unique_ptr<pas_model>* out) {
   pas_status st = validate(p);
   if (st != PAS_OK) return st;
   std::unique_ptr<pas_model> m(new pas_model());
@@ -932,6 +936,19 @@ pas_status pas_model_create(const pas_model_params* p, pas_model** out) {
     luminance_factors(m->wavelengths, m->solar, -3.0, m->sky_k);
   }
   luminance_factors(m->wavelengths, m->solar, 0.0, m->sun_k);
+  *out = std::move(m);
+  return PAS_OK;
+}
+}  // namespace
+
+extern "C" {
+
+pas_status pas_model_create(const pas_model_params* p, pas_model** out) {
+  if (out == nullptr) return fail(PAS_ERR_INVALID_ARGUMENT, "out_model is NULL");
+  *out = nullptr;
+  std::unique_ptr<pas_model> m;
+  pas_status st = build_host_model(p, &m);
+  if (st != PAS_OK) return st;
 
   // ---- device ----
   int count = 0;
@@ -2031,46 +2048,18 @@ pas_status pas_model_get_sun_and_sky_irradiance(pas_model* m, int use_luminance,
   return PAS_OK;
 }
 
-pas_status pas_model_render_scene(pas_model* m, const pas_scene_view* v, float* rgb, uint32_t* argb) {
-  if (v == nullptr) return fail(PAS_ERR_INVALID_ARGUMENT, "view is NULL");
-  pas_status st = render_ready(m, v->use_luminance);
+pas_status pas_model_render_context(pas_model* m, int use_luminance, void* out, size_t* bytes) {
+  if (bytes == nullptr) return fail(PAS_ERR_INVALID_ARGUMENT, "NULL argument");
+  if (out == nullptr) {
+    *bytes = sizeof(pas::RenderContext);
+    return PAS_OK;
+  }
+  pas_status st = render_ready(m, use_luminance);
   if (st != PAS_OK) return st;
-  if (v->width < 1 || v->height < 1 || (size_t)v->width * v->height > ((size_t)1 << 28)) {
-    return fail(PAS_ERR_INVALID_ARGUMENT, "bad image size");
-  }
-  if (!(v->sphere_radius > 0.0) || !(v->sun_size[0] > 0.0)) {
-    return fail(PAS_ERR_INVALID_ARGUMENT, "sphere_radius and sun_size[0] must be positive");
-  }
-  if (rgb == nullptr && argb == nullptr) return fail(PAS_ERR_INVALID_ARGUMENT, "no output requested");
-  PAS_CUDA(cudaSetDevice(m->device));
-  pas::RenderView rv{};
-  std::memcpy(rv.camera, v->camera, sizeof rv.camera);
-  std::memcpy(rv.earth_center, v->earth_center, sizeof rv.earth_center);
-  std::memcpy(rv.sun_direction, v->sun_direction, sizeof rv.sun_direction);
-  std::memcpy(rv.sun_size, v->sun_size, sizeof rv.sun_size);
-  std::memcpy(rv.sphere_center, v->sphere_center, sizeof rv.sphere_center);
-  rv.sphere_radius = v->sphere_radius;
-  std::memcpy(rv.model_from_clip, v->model_from_clip, sizeof rv.model_from_clip);
-  std::memcpy(rv.ground_albedo, v->ground_albedo, sizeof rv.ground_albedo);
-  std::memcpy(rv.sphere_albedo, v->sphere_albedo, sizeof rv.sphere_albedo);
-  rv.exposure = v->exposure;
-  rv.width = v->width;
-  rv.height = v->height;
-  const size_t pixels = (size_t)v->width * v->height;
-  void *d_rgb, *d_argb;
-  if ((st = stage_out(m, 0, rgb, pixels * 3 * sizeof(float), &d_rgb)) != PAS_OK) return st;
-  if ((st = stage_out(m, 1, argb, pixels * sizeof(uint32_t), &d_argb)) != PAS_OK) return st;
-  {
-    RenderTimer timer(m);
-    cudaError_t e = pas::launch_render_scene(m->geom, render_tables(m), render_constants(m, v->use_luminance),
-                                             rv, static_cast<float*>(d_rgb), static_cast<unsigned*>(d_argb),
-                                             m->stream);
-    timer.stop();
-    PAS_CUDA(e);
-  }
-  if ((st = unstage_out(m, rgb, d_rgb, pixels * 3 * sizeof(float))) != PAS_OK) return st;
-  if ((st = unstage_out(m, argb, d_argb, pixels * sizeof(uint32_t))) != PAS_OK) return st;
-  PAS_CUDA(cudaStreamSynchronize(m->stream));
+  if (*bytes < sizeof(pas::RenderContext)) return fail(PAS_ERR_INVALID_ARGUMENT, "context buffer too small");
+  const pas::RenderContext ctx{m->geom, render_tables(m), render_constants(m, use_luminance)};
+  std::memcpy(out, &ctx, sizeof ctx);
+  *bytes = sizeof ctx;
   return PAS_OK;
 }
 
@@ -2192,11 +2181,8 @@ std::string api_wrappers() {
 
 }  // namespace
 
-extern "C" pas_status pas_model_shader_source(const pas_model* m, const char* glsl_directory,
-                                              char* buffer, size_t* size) {
-  if (m == nullptr || glsl_directory == nullptr || size == nullptr) {
-    return fail(PAS_ERR_INVALID_ARGUMENT, "NULL argument");
-  }
+namespace {
+pas_status shader_source(const pas_model* m, const char* glsl_directory, std::string* out) {
   std::string definitions, functions;
   const std::string dir(glsl_directory);
   if (!read_text(dir + "/definitions.glsl", &definitions) || !read_text(dir + "/functions.glsl", &functions)) {
@@ -2232,6 +2218,11 @@ extern "C" pas_status pas_model_shader_source(const pas_model* m, const char* gl
   src += functions;
   if (m->num_precomputed_wavelengths <= 3) src += "#define RADIANCE_API_ENABLED\n";
   src += api_wrappers();
+  *out = std::move(src);
+  return PAS_OK;
+}
+
+pas_status copy_out(const std::string& src, char* buffer, size_t* size) {
   const size_t need = src.size() + 1;
   if (buffer == nullptr) {
     *size = need;
@@ -2242,3 +2233,53 @@ extern "C" pas_status pas_model_shader_source(const pas_model* m, const char* gl
   *size = need;
   return PAS_OK;
 }
+
+pas_status write_text(const std::string& path, const std::string& text) {
+  std::ofstream out(path);
+  out << text;
+  out.close();
+  return out ? PAS_OK : fail(PAS_ERR_IO, "cannot write " + path);
+}
+}  // namespace
+
+extern "C" {
+
+pas_status pas_model_shader_source(const pas_model* m, const char* glsl_directory, char* buffer, size_t* size) {
+  if (m == nullptr || glsl_directory == nullptr || size == nullptr) {
+    return fail(PAS_ERR_INVALID_ARGUMENT, "NULL argument");
+  }
+  std::string src;
+  pas_status st = shader_source(m, glsl_directory, &src);
+  return st != PAS_OK ? st : copy_out(src, buffer, size);
+}
+
+pas_status pas_shader_source(const pas_model_params* params, const char* glsl_directory, char* buffer,
+                             size_t* size) {
+  if (glsl_directory == nullptr || size == nullptr) return fail(PAS_ERR_INVALID_ARGUMENT, "NULL argument");
+  std::unique_ptr<pas_model> m;
+  pas_status st = build_host_model(params, &m);
+  if (st != PAS_OK) return st;
+  std::string src;
+  st = shader_source(m.get(), glsl_directory, &src);
+  return st != PAS_OK ? st : copy_out(src, buffer, size);
+}
+
+pas_status pas_model_save_webgl(pas_model* m, const char* directory, const char* glsl_directory,
+                                const char* vertex_shader_source, const char* fragment_shader_source) {
+  if (m == nullptr || directory == nullptr || glsl_directory == nullptr) {
+    return fail(PAS_ERR_INVALID_ARGUMENT, "NULL argument");
+  }
+  pas_status st = pas_model_save_dat(m, directory);
+  if (st != PAS_OK) return st;
+  std::string src;
+  if ((st = shader_source(m, glsl_directory, &src)) != PAS_OK) return st;
+  const std::string dir(directory);
+  if ((st = write_text(dir + "/atmosphere_shader.txt", src)) != PAS_OK) return st;
+  if (vertex_shader_source != nullptr &&
+      (st = write_text(dir + "/vertex_shader.txt", vertex_shader_source)) != PAS_OK) return st;
+  if (fragment_shader_source != nullptr &&
+      (st = write_text(dir + "/fragment_shader.txt", fragment_shader_source)) != PAS_OK) return st;
+  return PAS_OK;
+}
+
+}  // extern "C"

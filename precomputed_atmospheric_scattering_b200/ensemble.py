@@ -1,6 +1,7 @@
 """Batches of atmospheres (BASELINE config 5): a turbidity x ozone x ground-albedo sweep of the demo's
 Earth, precomputed with several models in flight at once (pas_model_init_async: every model has its
-own CUDA streams, their kernels share the GPU), then rendered with the model_test.glsl scene kernel.
+own CUDA streams, their kernels share the GPU); the tables are then used through the render-time
+lookups (Model.GetSkyRadiance ...), by the tests through the reference's test scene (tests/scene_render.py).
 
 The reference has no batch API: its demo re-creates one Model per settings change
 (atmosphere/demo/demo.cc:446-494). The sweep below varies what the demo's keys vary -- the Mie scale
@@ -66,15 +67,3 @@ def precompute(specs: Sequence[AtmosphereSpec], num_scattering_orders: int = 4, 
             m.close()
         raise
     return models
-
-
-def render(models: Sequence[Model], view, use_luminance: Optional[bool] = None) -> np.ndarray:
-    """The test scene of reference/model_test.glsl rendered with every model's tables:
-    float32 [n, height, width, 3] (before tone mapping)."""
-    out = None
-    for i, m in enumerate(models):
-        rgb, _ = m.render_scene(view)
-        if out is None:
-            out = np.empty((len(models),) + rgb.shape, dtype=np.float32)
-        out[i] = rgb
-    return out

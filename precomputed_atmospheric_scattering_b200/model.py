@@ -61,16 +61,6 @@ class _Params(ctypes.Structure):
         ("half_precision", ctypes.c_int), ("sizes", _Sizes), ("device", ctypes.c_int)]
 
 
-class _SceneView(ctypes.Structure):
-    """pas_scene_view (include/pas_b200.h)."""
-    _fields_ = [("camera", ctypes.c_double * 3), ("earth_center", ctypes.c_double * 3),
-                ("sun_direction", ctypes.c_double * 3), ("sun_size", ctypes.c_double * 2),
-                ("sphere_center", ctypes.c_double * 3), ("sphere_radius", ctypes.c_double),
-                ("model_from_clip", ctypes.c_double * 9), ("ground_albedo", ctypes.c_double * 3),
-                ("sphere_albedo", ctypes.c_double * 3), ("exposure", ctypes.c_double),
-                ("use_luminance", ctypes.c_int), ("width", ctypes.c_int), ("height", ctypes.c_int)]
-
-
 class _TextureInfo(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int) for n in
                 ("width", "height", "depth", "channels", "bytes_per_channel", "present")]
@@ -104,6 +94,8 @@ def load_library() -> ctypes.CDLL:
         lib.pas_model_read_texture.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t]
         lib.pas_model_save_dat.argtypes = [ctypes.c_void_p, ctypes.c_char_p]
         lib.pas_model_shader_source.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_void_p, ctypes.POINTER(ctypes.c_size_t)]
+        lib.pas_shader_source.argtypes = [ctypes.POINTER(_Params), ctypes.c_char_p, ctypes.c_void_p, ctypes.POINTER(ctypes.c_size_t)]
+        lib.pas_model_save_webgl.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p]
         lib.pas_model_luminance_factors.argtypes = [ctypes.c_void_p, _DP]
         lib.pas_convert_spectrum_to_linear_srgb.argtypes = [ctypes.c_size_t, _DP, _DP, _DP, _DP, _DP]
         lib.pas_model_channels.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int), _DP]
@@ -133,8 +125,8 @@ def load_library() -> ctypes.CDLL:
         lib.pas_model_get_sun_and_sky_irradiance.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t,
                                                              ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                                              ctypes.c_void_p, ctypes.c_void_p]
-        lib.pas_model_render_scene.argtypes = [ctypes.c_void_p, ctypes.POINTER(_SceneView), ctypes.c_void_p,
-                                               ctypes.c_void_p]
+        lib.pas_model_render_context.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
+                                                 ctypes.POINTER(ctypes.c_size_t)]
         lib.pas_model_last_render_ms.argtypes = [ctypes.c_void_p, _FP]
         _lib = lib
     return _lib
@@ -204,6 +196,62 @@ def spectral_channels(num_precomputed_wavelengths: int):
     return lam, lum
 
 
+def _make_params(wavelengths, solar_irradiance, sun_angular_radius, bottom_radius, top_radius,
+                 rayleigh_density, rayleigh_scattering, mie_density, mie_scattering, mie_extinction,
+                 mie_phase_function_g, absorption_density, absorption_extinction, ground_albedo,
+                 max_sun_zenith_angle, length_unit_in_meters, num_precomputed_wavelengths,
+                 combine_scattering_textures, half_precision, sizes=None, device=None):
+    """pas_model_params from the 19 constructor arguments; returns (params, objects to keep alive)."""
+    keep = []
+    p = _Params()
+    p.num_wavelengths = len(wavelengths)
+    for name, v in (("wavelengths", wavelengths), ("solar_irradiance", solar_irradiance),
+                    ("rayleigh_scattering", rayleigh_scattering), ("mie_scattering", mie_scattering),
+                    ("mie_extinction", mie_extinction),
+                    ("absorption_extinction", absorption_extinction), ("ground_albedo", ground_albedo)):
+        if len(v) != len(wavelengths):
+            raise ValueError(f"{name} must have one value per wavelength")  # model.cc:539
+        a, ptr = _darr(v)
+        keep.append(a)
+        setattr(p, name, ptr)
+    p.sun_angular_radius, p.bottom_radius, p.top_radius = sun_angular_radius, bottom_radius, top_radius
+    for name, layers in (("rayleigh", rayleigh_density), ("mie", mie_density),
+                         ("absorption", absorption_density)):
+        arr = _layers(layers)
+        keep.append(arr)
+        setattr(p, f"num_{name}_layers", len(layers))
+        setattr(p, f"{name}_density", ctypes.cast(arr, _LP))
+    p.mie_phase_function_g = mie_phase_function_g
+    p.max_sun_zenith_angle, p.length_unit_in_meters = max_sun_zenith_angle, length_unit_in_meters
+    p.num_precomputed_wavelengths = int(num_precomputed_wavelengths)
+    p.combine_scattering_textures = int(bool(combine_scattering_textures))
+    p.half_precision = int(bool(half_precision))
+    for k, v in (sizes or {}).items():
+        setattr(p.sizes, k, int(v))
+    p.device = 0 if device is None else device + 1
+    return p, keep
+
+
+def shader_source(spec: AtmosphereSpec, glsl_directory: str, sizes: Optional[Dict[str, int]] = None) -> str:
+    """The GLSL source atmosphere::Model::shader() compiles, from the constructor parameters alone
+    (pas_shader_source): needs neither a model nor a GPU -- the reference compiles it in its
+    constructor, before Init (atmosphere/model.cc:769-776)."""
+    lib = load_library()
+    p, keep = _make_params(spec.wavelengths, spec.solar_irradiance, spec.sun_angular_radius, spec.bottom_radius,
+                           spec.top_radius, spec.rayleigh_density, spec.rayleigh_scattering, spec.mie_density,
+                           spec.mie_scattering, spec.mie_extinction, spec.mie_phase_function_g,
+                           spec.absorption_density, spec.absorption_extinction, spec.ground_albedo,
+                           spec.max_sun_zenith_angle, spec.length_unit_in_meters,
+                           spec.num_precomputed_wavelengths, spec.combine_scattering_textures,
+                           spec.half_precision, sizes)
+    n = ctypes.c_size_t()
+    d = glsl_directory.encode()
+    _check(lib.pas_shader_source(ctypes.byref(p), d, None, ctypes.byref(n)))
+    buf = ctypes.create_string_buffer(n.value)
+    _check(lib.pas_shader_source(ctypes.byref(p), d, buf, ctypes.byref(n)))
+    return buf.value.decode("utf-8")
+
+
 class Model:
     """Same 19 constructor arguments as atmosphere::Model (atmosphere/model.h:182-281), plus the
     run-time extensions of the C ABI (`sizes`, `device`)."""
@@ -218,33 +266,12 @@ class Model:
                  device: Optional[int] = None):
         self._lib = load_library()
         self._h = ctypes.c_void_p()
-        keep = []
-        p = _Params()
-        p.num_wavelengths = len(wavelengths)
-        for name, v in (("wavelengths", wavelengths), ("solar_irradiance", solar_irradiance),
-                        ("rayleigh_scattering", rayleigh_scattering), ("mie_scattering", mie_scattering),
-                        ("mie_extinction", mie_extinction),
-                        ("absorption_extinction", absorption_extinction), ("ground_albedo", ground_albedo)):
-            if len(v) != len(wavelengths):
-                raise ValueError(f"{name} must have one value per wavelength")  # model.cc:539
-            a, ptr = _darr(v)
-            keep.append(a)
-            setattr(p, name, ptr)
-        p.sun_angular_radius, p.bottom_radius, p.top_radius = sun_angular_radius, bottom_radius, top_radius
-        for name, layers in (("rayleigh", rayleigh_density), ("mie", mie_density),
-                             ("absorption", absorption_density)):
-            arr = _layers(layers)
-            keep.append(arr)
-            setattr(p, f"num_{name}_layers", len(layers))
-            setattr(p, f"{name}_density", ctypes.cast(arr, _LP))
-        p.mie_phase_function_g = mie_phase_function_g
-        p.max_sun_zenith_angle, p.length_unit_in_meters = max_sun_zenith_angle, length_unit_in_meters
-        p.num_precomputed_wavelengths = int(num_precomputed_wavelengths)
-        p.combine_scattering_textures = int(bool(combine_scattering_textures))
-        p.half_precision = int(bool(half_precision))
-        for k, v in (sizes or {}).items():
-            setattr(p.sizes, k, int(v))
-        p.device = 0 if device is None else device + 1
+        p, keep = _make_params(wavelengths, solar_irradiance, sun_angular_radius, bottom_radius, top_radius,
+                               rayleigh_density, rayleigh_scattering, mie_density, mie_scattering,
+                               mie_extinction, mie_phase_function_g, absorption_density, absorption_extinction,
+                               ground_albedo, max_sun_zenith_angle, length_unit_in_meters,
+                               num_precomputed_wavelengths, combine_scattering_textures, half_precision,
+                               sizes, device)
         _check(self._lib.pas_model_create(ctypes.byref(p), ctypes.byref(self._h)))
         self.half_precision = bool(half_precision)
         self.combine_scattering_textures = bool(combine_scattering_textures)
@@ -355,6 +382,16 @@ class Model:
         return self._sky(self._lib.pas_model_get_sky_radiance_to_point, camera, point, shadow_length,
                          sun_direction, use_luminance)
 
+    def sky_radiance_device(self, n: int, camera_ptr: int, view_ray_ptr: int, shadow_length_ptr: int,
+                            sun_direction_ptr: int, radiance_ptr: int, transmittance_ptr: int = 0,
+                            use_luminance: bool = False) -> None:
+        """pas_model_get_sky_radiance on DEVICE arrays (raw pointers: [n][3] float64 inputs, [n] float64
+        shadow lengths or 0, [n][3] float32 outputs): nothing crosses PCIe."""
+        p = lambda v: ctypes.c_void_p(int(v) or None)
+        _check(self._lib.pas_model_get_sky_radiance(self._h, int(use_luminance), int(n), p(camera_ptr),
+                                                   p(view_ray_ptr), p(shadow_length_ptr), p(sun_direction_ptr),
+                                                   p(radiance_ptr), p(transmittance_ptr)))
+
     def GetSunAndSkyIrradiance(self, point, normal, sun_direction, use_luminance: bool = False):
         """Batched GetSunAndSkyIrradiance (functions.glsl:1878-1896): returns (sun, sky)."""
         p = self._vec3(point)
@@ -366,21 +403,14 @@ class Model:
                                                              e1.ctypes.data))
         return e0, e1
 
-    def render_scene(self, view, want_argb: bool = True):
-        """Renders the reference's test scene (reference/model_test.glsl) for a scene.SceneView.
-        Returns (rgb float32 [H, W, 3] before tone mapping, argb uint32 [H, W] or None)."""
-        v = _SceneView()
-        for name in ("camera", "earth_center", "sun_direction", "sun_size", "sphere_center",
-                     "model_from_clip", "ground_albedo", "sphere_albedo"):
-            vals = list(getattr(view, name))
-            getattr(v, name)[:] = vals
-        v.sphere_radius, v.exposure = view.sphere_radius, view.exposure
-        v.use_luminance, v.width, v.height = int(view.use_luminance), view.width, view.height
-        rgb = np.empty((view.height, view.width, 3), np.float32)
-        argb = np.empty((view.height, view.width), np.uint32) if want_argb else None
-        _check(self._lib.pas_model_render_scene(self._h, ctypes.byref(v), rgb.ctypes.data,
-                                                argb.ctypes.data if want_argb else None))
-        return rgb, argb
+    def render_context(self, use_luminance: bool = False) -> bytes:
+        """The pas::RenderContext of csrc/kernel_render.cuh for this model (pas_model_render_context): what
+        a CUDA renderer passes to its own kernels to call the lookups on the device."""
+        n = ctypes.c_size_t()
+        _check(self._lib.pas_model_render_context(self._h, int(use_luminance), None, ctypes.byref(n)))
+        buf = ctypes.create_string_buffer(n.value)
+        _check(self._lib.pas_model_render_context(self._h, int(use_luminance), buf, ctypes.byref(n)))
+        return buf.raw[:n.value]
 
     def last_render_ms(self) -> float:
         ms = ctypes.c_float(0)
@@ -426,6 +456,14 @@ class Model:
     @property
     def single_mie_scattering(self):
         return self.texture(TEXTURE_SINGLE_MIE)
+
+    def save_webgl(self, directory: str, glsl_directory: str, vertex_shader: Optional[str] = None,
+                   fragment_shader: Optional[str] = None) -> None:
+        """The WebGL hand-off of atmosphere/demo/webgl/precompute.cc:81-106: the .dat files,
+        atmosphere_shader.txt and (the caller's own) vertex_shader.txt / fragment_shader.txt."""
+        enc = lambda t: None if t is None else t.encode()
+        _check(self._lib.pas_model_save_webgl(self._h, directory.encode(), glsl_directory.encode(),
+                                              enc(vertex_shader), enc(fragment_shader)))
 
     def save_dat(self, directory: str) -> None:
         _check(self._lib.pas_model_save_dat(self._h, directory.encode()))

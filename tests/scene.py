@@ -1,5 +1,6 @@
-"""The view / scene description consumed by ``Model.render_scene`` (C ABI ``pas_scene_view``), with
-the reference's integration-test scene as the canonical instance.
+"""TEST INFRASTRUCTURE: the view / scene description consumed by tests/scene_render.py (the CUDA scene
+kernel of tests/cuda/scene_kernel.cu) and by the oracle's renderer, with the reference's
+integration-test scene as the canonical instance.
 
 The scene is the one of atmosphere/reference/model_test.glsl: a sphere S resting on a spherical
 planet P, lit by the sun and the sky, seen through the atmosphere with light shafts. Camera, view

@@ -15,6 +15,8 @@ match the oracle renderer on the same tables.
 import numpy as np
 import pytest
 
+from tests import scene, scene_render
+
 from tests import parity
 from tests.test_gpu_parity import assert_close, oracle_for, oracle_sizes
 
@@ -157,15 +159,15 @@ def test_config5_full_size_batch_and_renders(pas, orc):
     specs = pas.ensemble.sweep(half_precision=False, sun_angular_radius=0.2678 * np.pi / 180.0,
                                max_sun_zenith_deg=102.0)
     models = pas.ensemble.precompute(specs, 4)
-    view = pas.scene.model_test_view(65.0, 90.0, False, width=1920, height=1080,
+    view = scene.model_test_view(65.0, 90.0, False, width=1920, height=1080,
                                      sun_angular_radius=specs[0].sun_angular_radius)
-    images = pas.ensemble.render(models, view)
+    images = np.stack([scene_render.render_scene(m, view, want_argb=False)[0] for m in models])
     assert images.shape == (64, 1080, 1920, 3) and np.isfinite(images).all()
     assert len({float(im.sum()) for im in images}) == 64          # 64 different skies
-    small = pas.scene.model_test_view(65.0, 90.0, False, width=160, height=90,
+    small = scene.model_test_view(65.0, 90.0, False, width=160, height=90,
                                       sun_angular_radius=specs[0].sun_angular_radius)
     for idx in (0, 22, 41, 63):
-        rgb, _ = models[idx].render_scene(small)
+        rgb, _ = scene_render.render_scene(models[idx], small)
         want = oracle_renderer(pas, orc, specs[idx], models[idx], False).render_scene(small)
         assert image_rel_error(rgb, want) < 1e-5
     for m in models:

@@ -365,6 +365,22 @@ def test_dat_export_and_device_pointers(pas, tmp_path):
                     ("irradiance.dat", model.irradiance)):
         raw = np.fromfile(os.path.join(tmp_path, fn), dtype="<f4")
         assert raw.size == tab.size and np.array_equal(raw.reshape(tab.shape), tab)
+    # the whole WebGL hand-off (demo/webgl/precompute.cc:81-106): .dat files + the three shader texts
+    web = tmp_path / "webgl"
+    web.mkdir()
+    glsl = tmp_path / "glsl"
+    glsl.mkdir()
+    (glsl / "definitions.glsl").write_text("// DEFINITIONS\n")
+    (glsl / "functions.glsl").write_text("// FUNCTIONS\n")
+    model.save_webgl(str(web), str(glsl), vertex_shader="// the demo's vertex shader\n",
+                     fragment_shader="// the demo's fragment shader\n")
+    assert sorted(os.listdir(web)) == ["atmosphere_shader.txt", "fragment_shader.txt", "irradiance.dat",
+                                       "scattering.dat", "transmittance.dat", "vertex_shader.txt"]
+    assert (web / "atmosphere_shader.txt").read_text() == model.GetShaderSource(str(glsl))
+    assert (web / "atmosphere_shader.txt").read_text() == pas.shader_source(pas.small_planet(), str(glsl), sizes=sizes)
+    assert (web / "vertex_shader.txt").read_text() == "// the demo's vertex shader\n"
+    assert np.array_equal(np.fromfile(web / "scattering.dat", dtype="<f4").reshape(model.scattering.shape), model.scattering)
+    model.save_webgl(str(web), str(glsl))          # the caller's shaders are optional
     assert model.device_ptr(pas.TEXTURE_SCATTERING) != 0
     with pytest.raises(AssertionError):
         model.texture(pas.TEXTURE_IRRADIANCE, out=np.empty(3, dtype=np.float32))

@@ -12,6 +12,8 @@ import math
 import numpy as np
 import pytest
 
+from tests import scene
+
 from oracle import ref
 
 needs_ref = pytest.mark.skipif(not ref.available(), reason="oracle/_ref/libpas_ref.so not built")
@@ -46,7 +48,7 @@ def rel(a, b, floor=1e-12):
 @pytest.mark.parametrize("zenith", [65.0, 88.0, 100.0])
 def test_scene_matches_the_reference_renderer(shared, zenith):
     pas, spec, model, o, r, _ = shared
-    view = pas.scene.model_test_view(zenith, 90.0, False, width=96, height=54,
+    view = scene.model_test_view(zenith, 90.0, False, width=96, height=54,
                                      sun_angular_radius=spec.sun_angular_radius)
     want = model.render_scene(view, view.ground_albedo, view.sphere_albedo)
     got = r.render_scene(view)
@@ -174,7 +176,7 @@ def test_luminance_factors_scale_the_outputs(pas, orc):
 
 
 def test_psnr_and_tone_map_follow_the_reference(pas):
-    scn = pas.scene
+    scn = scene
     rgb = np.zeros((2, 2, 3))
     rgb[0, 0] = [0.1, 0.2, 0.3]
     img = scn.tone_map(rgb, 10.0)

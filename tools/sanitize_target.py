@@ -11,6 +11,7 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import precomputed_atmospheric_scattering_b200 as pas  # noqa: E402
+from tests import scene, scene_render  # noqa: E402
 
 SIZES = dict(transmittance_width=256, transmittance_height=8, scattering_r=4, scattering_mu=8,
              scattering_mu_s=32, scattering_nu=8, irradiance_width=64, irradiance_height=4)
@@ -29,9 +30,9 @@ for _ in range(2):   # the second Init runs on recycled, dirty buffers
     model.Init(3)
 S = model.texture(pas.TEXTURE_SCATTERING, as_float32=False)
 assert np.array_equal(S, host[pas.TEXTURE_SCATTERING]) and np.isfinite(S.astype(np.float32)).all()
-view = pas.scene.model_test_view(65.0, 90.0, spec.num_precomputed_wavelengths > 3, width=64, height=36,
+view = scene.model_test_view(65.0, 90.0, spec.num_precomputed_wavelengths > 3, width=64, height=36,
                                  sun_angular_radius=spec.sun_angular_radius)
-rgb, _ = model.render_scene(view)
+rgb, _ = scene_render.render_scene(model, view)
 assert np.isfinite(rgb).all()
 print("sanitize target ok:", model.last_launch_count(), "launches,", {k: round(v, 3) for k, v in model.last_timings().items()})
 model.close()
