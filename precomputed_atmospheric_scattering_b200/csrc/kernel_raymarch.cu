@@ -368,6 +368,31 @@ multiple_scattering_kernel(const __grid_constant__ PasGeometry g,
              fin.half_precision, true);
 }
 
+// ---- per-ray setup tables ------------------------------------------------------------------------------
+// Everything a ray-march block computes before its sample loop depends on the ray (layer k, mu row j)
+// and on the transmittance table only -- not on the scattering order: the 51 sample records, the path
+// transmittances Tw[sample][channel], the on-slab permutation of the row's texels. Computed inside the
+// kernels it is a latency-bound prologue (fp64 geometry on 51 threads, then 51 x 16 ratios of bilinear
+// fp64 fetches) that costs 0.19 of the 0.94 ms of a multiple-scattering pass. ray_setup_kernel runs
+// the SAME code once per Init and channel group and leaves the results in HBM (9 KB per ray, 36 MB);
+// the single-scattering pass and every multiple-scattering pass then start by copying them in.
+struct RaySetupLayout {
+  size_t plan, sun, tw, perm, stride;   // byte offsets inside a ray's record, record size
+};
+__host__ __device__ inline RaySetupLayout ray_setup_layout(int cp) {
+  RaySetupLayout l;
+  l.plan = 0;
+  l.sun = l.plan + kSamples * 48;
+  l.tw = l.sun + kSamples * 48;
+  l.perm = l.tw + (size_t)kSamples * cp * sizeof(float);
+  l.stride = (l.perm + 256 * sizeof(int) + 15) & ~(size_t)15;
+  return l;
+}
+// block-wide copy of n 16-byte vectors
+__device__ __forceinline__ void copy16(void* dst, const void* src, int n, int tid, int nthreads) {
+  for (int i = tid; i < n; i += nthreads) reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(src)[i];
+}
+
 // ---- multiple scattering, reference row width (256 texels = block size) -------------------------
 // Same mapping as above, with two changes that cut the L1 data-pipe wavefronts (the bound of this
 // kernel):
@@ -389,29 +414,16 @@ struct __align__(16) SlotSample {
   int pad;
 };
 
-template <int NC>
-__global__ void __launch_bounds__(256, 2)
-multiple_scattering_rows_kernel(const __grid_constant__ PasGeometry g,
-                                const __grid_constant__ PasSpectrum sp, const float* __restrict__ T,
-                                const float* __restrict__ dJ, float* __restrict__ dS,
-                                FinalTables fin, int k_begin, int k_stride) {
-  constexpr int CP = PAS_CHANNEL_PITCH(NC), Q = CP / 4, WIDTH = 256;
-  static_assert(sizeof(SlotSample) == sizeof(ScatterSample), "plan is rewritten in place");
-  extern __shared__ __align__(16) float smem_dyn[];
-  __shared__ ScatterSample sSample[kSamples];
-  __shared__ __align__(16) float sTw[kSamples][CP];
-  __shared__ int sPerm[WIDTH];
-  __shared__ int sCount[WIDTH / 32];
-
-  const int tid = threadIdx.x;
-  const int j = blockIdx.x, k = k_begin + blockIdx.y * k_stride;
+// Prologue of a multiple-scattering block for the ray (layer k, mu row j): leaves the slot plan in
+// sSample (as SlotSample), the path transmittances in sTw and the on-slab permutation in sPerm.
+// (WITH_TW = false: the caller already holds the path transmittances, which do not depend on the pass.)
+template <int NC, bool WITH_TW = true>
+__device__ void rows_prologue(const PasGeometry& g, const float* __restrict__ T, const BlockRay& ray, int tid,
+                              ScatterSample* sSample, float (*sTw)[PAS_CHANNEL_PITCH(NC)], int* sPerm,
+                              int* sCount) {
+  constexpr int WIDTH = 256;
   const int mu_n = g.sz.mu_n, nu_n = g.sz.nu_n, mu_s_n = g.sz.mu_s_n;
-  constexpr int pitch = ((WIDTH + 7) & ~7) + 8 / Q;
-  float4* sRow = reinterpret_cast<float4*>(smem_dyn);  // [2][Q * pitch]
-  const float4* dJ4 = reinterpret_cast<const float4*>(dJ);
-
   __shared__ PathTaps sTaps[kSamples];
-  const BlockRay ray = block_ray(g, k, j);
   if (tid < kSamples) {
     ray_sample_geometry(g, ray.r, ray.rho, ray.mu, ray.hit, ray.d_end, tid, &sSample[tid], &sTaps[tid]);
   }
@@ -439,7 +451,7 @@ multiple_scattering_rows_kernel(const __grid_constant__ PasGeometry g,
     sPerm[pos] = tid;
   }
   // (the barrier inside the permutation published the taps of phase A)
-  ray_sample_transmittance<NC>(g, T, sTaps, sTw, tid, WIDTH);
+  if (WITH_TW) ray_sample_transmittance<NC>(g, T, sTaps, sTw, tid, WIDTH);
   // ---- slot plan ---------------------------------------------------------------------------------
   // Row (layer k, mu row j) always lives in slot 2 (k & 1) + (j & 1): the four corner rows of a sample
   // fall in four different slots, and a row shared with the previous sample is found where it was.
@@ -483,6 +495,41 @@ multiple_scattering_rows_kernel(const __grid_constant__ PasGeometry g,
     plan_w[tid].mask = mask;
   }
   __syncthreads();
+}
+
+template <int NC>
+__global__ void __launch_bounds__(256, 2)
+multiple_scattering_rows_kernel(const __grid_constant__ PasGeometry g,
+                                const __grid_constant__ PasSpectrum sp, const float* __restrict__ T,
+                                const float* __restrict__ dJ, float* __restrict__ dS,
+                                FinalTables fin, int k_begin, int k_stride, const char* __restrict__ setup) {
+  constexpr int CP = PAS_CHANNEL_PITCH(NC), Q = CP / 4, WIDTH = 256;
+  static_assert(sizeof(SlotSample) == sizeof(ScatterSample), "plan is rewritten in place");
+  extern __shared__ __align__(16) float smem_dyn[];
+  __shared__ ScatterSample sSample[kSamples];
+  __shared__ __align__(16) float sTw[kSamples][CP];
+  __shared__ int sPerm[WIDTH];
+  __shared__ int sCount[WIDTH / 32];
+
+  const int tid = threadIdx.x;
+  const int j = blockIdx.x, k = k_begin + blockIdx.y * k_stride;
+  const int mu_n = g.sz.mu_n, nu_n = g.sz.nu_n, mu_s_n = g.sz.mu_s_n;
+  constexpr int pitch = ((WIDTH + 7) & ~7) + 8 / Q;
+  float4* sRow = reinterpret_cast<float4*>(smem_dyn);  // [2][Q * pitch]
+  const float4* dJ4 = reinterpret_cast<const float4*>(dJ);
+
+  const BlockRay ray = block_ray(g, k, j);
+  if (setup != nullptr) {
+    // the prologue was run once for all passes by ray_setup_kernel
+    const RaySetupLayout lay = ray_setup_layout(CP);
+    const char* rec = setup + ((size_t)k * mu_n + j) * lay.stride;
+    copy16(sSample, rec + lay.plan, kSamples * 3, tid, WIDTH);
+    copy16(sTw, rec + lay.tw, kSamples * CP / 4, tid, WIDTH);
+    copy16(sPerm, rec + lay.perm, WIDTH / 4, tid, WIDTH);
+    __syncthreads();
+  } else {
+    rows_prologue<NC>(g, T, ray, tid, sSample, sTw, sPerm, sCount);
+  }
   const SlotSample* plan = reinterpret_cast<const SlotSample*>(sSample);
 
   // per-thread axes: mu_s (column) and nu (slab) of the texel this thread owns
@@ -609,49 +656,18 @@ multiple_scattering_rows_kernel(const __grid_constant__ PasGeometry g,
 // mu_s columns of one slab. The sun lookups of neighbouring lanes then fall on the same or on
 // neighbouring transmittance texels (they differ by d nu / r_i only), which the 128-bit shared loads
 // serve without bank conflicts; the staged row is stored unrotated.
-template <int NC, int MAXT, int MINB, int WIDTH, bool NU_LANES>
-__global__ void __launch_bounds__(MAXT, MINB)
-single_scattering_kernel(const __grid_constant__ PasGeometry g,
-                         const __grid_constant__ PasSpectrum sp, const float* __restrict__ T,
-                         float* __restrict__ dR, float* __restrict__ dM, FinalTables fin,
-                         int k_begin, int k_stride) {
-  constexpr int CP = PAS_CHANNEL_PITCH(NC), Q = CP / 4;
-  extern __shared__ __align__(16) float smem_dyn[];
-  __shared__ SunSample sSample[kSamples];
-  __shared__ __align__(16) float sTw[kSamples][CP];
-
-  const int tid = threadIdx.x;
-  const int j = blockIdx.x, k = k_begin + blockIdx.y * k_stride;
-  const int mu_n = g.sz.mu_n, nu_n = g.sz.nu_n, mu_s_n = g.sz.mu_s_n;
-  const int t_w = WIDTH > 0 ? WIDTH : g.sz.t_w;
-  const int width = WIDTH > 0 ? WIDTH : nu_n * mu_s_n;
-  const int nthreads = WIDTH > 0 ? WIDTH : (int)blockDim.x;
-  const int pitch = plane_pitch<Q>(t_w);
-  float4* sRow = reinterpret_cast<float4*>(smem_dyn);  // [2][Q * pitch]
-  const float4* T4 = reinterpret_cast<const float4*>(T);
-
+// Prologue of a single-scattering block for the ray (layer k, mu row j): the sample records in sSample
+// (with the transmittance-row slots to load in bits 16.. of y0 when the rows live in register slots) and
+// the path transmittances in sTw. Ends without a barrier: the caller's next one publishes the results.
+template <int NC, int WIDTH>
+__device__ void sun_prologue(const PasGeometry& g, const float* __restrict__ T, const BlockRay& ray, int tid,
+                             SunSample* sSample, float (*sTw)[PAS_CHANNEL_PITCH(NC)]) {
   __shared__ PathTaps sTaps[kSamples];
-  const BlockRay ray = block_ray(g, k, j);
   if (tid < kSamples) {
     ray_sample_geometry(g, ray.r, ray.rho, ray.mu, ray.hit, ray.d_end, tid, &sSample[tid], &sTaps[tid]);
   }
   __syncthreads();
   ray_sample_transmittance<NC>(g, T, sTaps, sTw, tid, (int)blockDim.x);
-  const int x = NU_LANES ? (tid % nu_n) * mu_s_n + tid / nu_n : tid;
-  const bool active = x < width;
-  const int i_nu = active ? x / mu_s_n : 0, i_mu_s = active ? x % mu_s_n : 0;
-  const double mu_s_d = scattering_col_mu_s(g, i_mu_s);
-  const double nu_d = scattering_slab_nu(g, i_nu, ray.mu, mu_s_d);
-  const float nu = (float)nu_d;
-  const float r_mu_s = (float)(ray.r * mu_s_d);
-  const float x_max = (float)(t_w - 1);
-  auto rot = [](int v) { return NU_LANES ? v : rot8(v); };
-
-  float4 accR[Q], accM[Q];
-#pragma unroll
-  for (int q = 0; q < Q; ++q) accR[q] = accM[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-  __syncthreads();
-
   // Reference row width (WIDTH > 0): the two transmittance rows bracketing r_i live in two register
   // slots, even rows in A and odd rows in B. A row shared with the previous sample is not read again
   // (about half of them), and the rows of sample i + 1 are requested right after the staged row of
@@ -673,8 +689,55 @@ single_scattering_kernel(const __grid_constant__ PasGeometry g,
     }
     __syncthreads();
     if (tid < kSamples) sSample[tid].y0 |= mask << 16;
-    __syncthreads();
   }
+
+}
+
+template <int NC, int MAXT, int MINB, int WIDTH, bool NU_LANES>
+__global__ void __launch_bounds__(MAXT, MINB)
+single_scattering_kernel(const __grid_constant__ PasGeometry g,
+                         const __grid_constant__ PasSpectrum sp, const float* __restrict__ T,
+                         float* __restrict__ dR, float* __restrict__ dM, FinalTables fin,
+                         int k_begin, int k_stride, const char* __restrict__ setup) {
+  constexpr int CP = PAS_CHANNEL_PITCH(NC), Q = CP / 4;
+  extern __shared__ __align__(16) float smem_dyn[];
+  __shared__ SunSample sSample[kSamples];
+  __shared__ __align__(16) float sTw[kSamples][CP];
+
+  const int tid = threadIdx.x;
+  const int j = blockIdx.x, k = k_begin + blockIdx.y * k_stride;
+  const int mu_n = g.sz.mu_n, nu_n = g.sz.nu_n, mu_s_n = g.sz.mu_s_n;
+  const int t_w = WIDTH > 0 ? WIDTH : g.sz.t_w;
+  const int width = WIDTH > 0 ? WIDTH : nu_n * mu_s_n;
+  const int nthreads = WIDTH > 0 ? WIDTH : (int)blockDim.x;
+  const int pitch = plane_pitch<Q>(t_w);
+  float4* sRow = reinterpret_cast<float4*>(smem_dyn);  // [2][Q * pitch]
+  const float4* T4 = reinterpret_cast<const float4*>(T);
+
+  const BlockRay ray = block_ray(g, k, j);
+  if (WIDTH > 0 && setup != nullptr) {
+    // the prologue was run once for all passes by ray_setup_kernel
+    const RaySetupLayout lay = ray_setup_layout(CP);
+    const char* rec = setup + ((size_t)k * mu_n + j) * lay.stride;
+    copy16(sSample, rec + lay.sun, kSamples * 3, tid, nthreads);
+    copy16(sTw, rec + lay.tw, kSamples * CP / 4, tid, nthreads);
+  } else {
+    sun_prologue<NC, WIDTH>(g, T, ray, tid, sSample, sTw);
+  }
+  const int x = NU_LANES ? (tid % nu_n) * mu_s_n + tid / nu_n : tid;
+  const bool active = x < width;
+  const int i_nu = active ? x / mu_s_n : 0, i_mu_s = active ? x % mu_s_n : 0;
+  const double mu_s_d = scattering_col_mu_s(g, i_mu_s);
+  const double nu_d = scattering_slab_nu(g, i_nu, ray.mu, mu_s_d);
+  const float nu = (float)nu_d;
+  const float r_mu_s = (float)(ray.r * mu_s_d);
+  const float x_max = (float)(t_w - 1);
+  auto rot = [](int v) { return NU_LANES ? v : rot8(v); };
+
+  float4 accR[Q], accM[Q];
+#pragma unroll
+  for (int q = 0; q < Q; ++q) accR[q] = accM[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+  __syncthreads();
 
   if (ray.d_end > 0.0) {
     float4 A[Q], B[Q];
@@ -783,6 +846,38 @@ single_scattering_kernel(const __grid_constant__ PasGeometry g,
   }
 }
 
+// ---- the ray setup pass -----------------------------------------------------------------------------------
+// One block per ray (layer k, mu row j): runs the prologues of the two ray-march kernels and stores their
+// results (RaySetupLayout). Same code, same arithmetic: a pass fed from the tables gives the bits it would
+// have computed itself.
+template <int NC>
+__global__ void __launch_bounds__(256, 4)
+ray_setup_kernel(const __grid_constant__ PasGeometry g, const float* __restrict__ T, char* __restrict__ setup,
+                 int k_begin, int k_stride, int with_rows) {
+  constexpr int CP = PAS_CHANNEL_PITCH(NC), WIDTH = 256;
+  __shared__ ScatterSample sSample[kSamples];
+  __shared__ SunSample sSun[kSamples];
+  __shared__ __align__(16) float sTw[kSamples][CP];
+  __shared__ __align__(16) int sPerm[WIDTH];
+  __shared__ int sCount[WIDTH / 32];
+  const int tid = threadIdx.x;
+  const int j = blockIdx.x, k = k_begin + blockIdx.y * k_stride;
+  const BlockRay ray = block_ray(g, k, j);
+  const RaySetupLayout lay = ray_setup_layout(CP);
+  char* rec = setup + ((size_t)k * g.sz.mu_n + j) * lay.stride;
+  // single scattering: records + path transmittances
+  sun_prologue<NC, WIDTH>(g, T, ray, tid, sSun, sTw);
+  __syncthreads();
+  copy16(rec + lay.sun, sSun, kSamples * 3, tid, WIDTH);
+  copy16(rec + lay.tw, sTw, kSamples * CP / 4, tid, WIDTH);
+  if (with_rows) {
+    // multiple scattering: slot plan + permutation (the path transmittances are the same numbers)
+    rows_prologue<NC, false>(g, T, ray, tid, sSample, sTw, sPerm, sCount);
+    copy16(rec + lay.plan, sSample, kSamples * 3, tid, WIDTH);
+    copy16(rec + lay.perm, sPerm, WIDTH / 4, tid, WIDTH);
+  }
+}
+
 inline int round_up32(int v) { return (v + 31) / 32 * 32; }
 
 // Rows of up to 256 texels (the reference's 8 x 32) run with 256-thread blocks and a register
@@ -799,7 +894,7 @@ cudaError_t prepare(Kern kern, size_t dyn) {
 template <int NC>
 cudaError_t launch_multiple_nc(const PasGeometry& g, const PasSpectrum& s, const float* T,
                                const float* dJ, float* dS, FinalTables fin, LayerSet layers,
-                               cudaStream_t stream) {
+                               cudaStream_t stream, const void* setup) {
   constexpr int CP = PAS_CHANNEL_PITCH(NC), Q = CP / 4;
   const int width = g.sz.nu_n * g.sz.mu_s_n;
   if (width > 1024) return cudaErrorInvalidValue;
@@ -811,7 +906,7 @@ cudaError_t launch_multiple_nc(const PasGeometry& g, const PasSpectrum& s, const
   if (width == 256 && Q > 1) {
     auto kern = multiple_scattering_rows_kernel<NC>;  // the reference's 8 x 32 row
     if ((e = prepare(kern, dyn)) != cudaSuccess) return e;
-    kern<<<grid, 256, dyn, stream>>>(g, s, T, dJ, dS, fin, layers.begin, layers.stride);
+    kern<<<grid, 256, dyn, stream>>>(g, s, T, dJ, dS, fin, layers.begin, layers.stride, static_cast<const char*>(setup));
   } else if (width == 256) {
     auto kern = multiple_scattering_kernel<NC, 256, 3, 256>;
     if ((e = prepare(kern, dyn)) != cudaSuccess) return e;
@@ -831,7 +926,7 @@ cudaError_t launch_multiple_nc(const PasGeometry& g, const PasSpectrum& s, const
 template <int NC>
 cudaError_t launch_single_nc(const PasGeometry& g, const PasSpectrum& s, const float* T, float* dR,
                              float* dM, FinalTables fin, LayerSet layers,
-                             cudaStream_t stream) {
+                             cudaStream_t stream, const void* setup) {
   constexpr int CP = PAS_CHANNEL_PITCH(NC), Q = CP / 4;
   const int width = g.sz.nu_n * g.sz.mu_s_n;
   if (width > 1024) return cudaErrorInvalidValue;
@@ -843,15 +938,15 @@ cudaError_t launch_single_nc(const PasGeometry& g, const PasSpectrum& s, const f
   if (width == 256 && g.sz.t_w == 256) {
     auto kern = single_scattering_kernel<NC, 256, 2, 256, true>;  // 128 registers: the row slots stay in registers
     if ((e = prepare(kern, dyn)) != cudaSuccess) return e;
-    kern<<<grid, 256, dyn, stream>>>(g, s, T, dR, dM, fin, layers.begin, layers.stride);
+    kern<<<grid, 256, dyn, stream>>>(g, s, T, dR, dM, fin, layers.begin, layers.stride, static_cast<const char*>(setup));
   } else if (threads <= 256) {
     auto kern = single_scattering_kernel<NC, 256, 3, 0, false>;
     if ((e = prepare(kern, dyn)) != cudaSuccess) return e;
-    kern<<<grid, threads, dyn, stream>>>(g, s, T, dR, dM, fin, layers.begin, layers.stride);
+    kern<<<grid, threads, dyn, stream>>>(g, s, T, dR, dM, fin, layers.begin, layers.stride, nullptr);
   } else {
     auto kern = single_scattering_kernel<NC, 1024, 1, 0, false>;
     if ((e = prepare(kern, dyn)) != cudaSuccess) return e;
-    kern<<<grid, threads, dyn, stream>>>(g, s, T, dR, dM, fin, layers.begin, layers.stride);
+    kern<<<grid, threads, dyn, stream>>>(g, s, T, dR, dM, fin, layers.begin, layers.stride, nullptr);
   }
   return cudaGetLastError();
 }
@@ -860,10 +955,10 @@ cudaError_t launch_single_nc(const PasGeometry& g, const PasSpectrum& s, const f
 
 cudaError_t launch_multiple_scattering(const PasGeometry& g, const PasSpectrum& s, const float* T,
                                        const float* dJ, float* dS, FinalTables fin, LayerSet layers,
-                                       cudaStream_t stream) {
+                                       cudaStream_t stream, const void* setup) {
   switch (s.nc) {
 #define PAS_CASE(N) \
-  case N: return launch_multiple_nc<N>(g, s, T, dJ, dS, fin, layers, stream);
+  case N: return launch_multiple_nc<N>(g, s, T, dJ, dS, fin, layers, stream, setup);
     PAS_CASE(3) PAS_CASE(4) PAS_CASE(8) PAS_CASE(15) PAS_CASE(16)
 #undef PAS_CASE
     default: return cudaErrorInvalidValue;
@@ -872,14 +967,36 @@ cudaError_t launch_multiple_scattering(const PasGeometry& g, const PasSpectrum& 
 
 cudaError_t launch_single_scattering(const PasGeometry& g, const PasSpectrum& s, const float* T,
                                      float* dR, float* dM, FinalTables fin, LayerSet layers,
-                                     cudaStream_t stream) {
+                                     cudaStream_t stream, const void* setup) {
   switch (s.nc) {
 #define PAS_CASE(N) \
-  case N: return launch_single_nc<N>(g, s, T, dR, dM, fin, layers, stream);
+  case N: return launch_single_nc<N>(g, s, T, dR, dM, fin, layers, stream, setup);
     PAS_CASE(3) PAS_CASE(4) PAS_CASE(8) PAS_CASE(15) PAS_CASE(16)
 #undef PAS_CASE
     default: return cudaErrorInvalidValue;
   }
+}
+
+// Setup tables of the ray-march passes (ray_setup_kernel): 0 bytes when the table sizes do not take the
+// register-slot kernels (row width and transmittance width of 256).
+size_t ray_setup_bytes(const PasGeometry& g, int nc) {
+  if (g.sz.nu_n * g.sz.mu_s_n != 256 || g.sz.t_w != 256) return 0;
+  return ray_setup_layout(PAS_CHANNEL_PITCH(nc)).stride * (size_t)g.sz.mu_n * g.sz.r_n;
+}
+
+cudaError_t launch_ray_setup(const PasGeometry& g, const PasSpectrum& s, const float* T, void* setup,
+                             LayerSet layers, cudaStream_t stream) {
+  if (ray_setup_bytes(g, s.nc) == 0 || layers.count() == 0) return cudaSuccess;
+  const dim3 grid(g.sz.mu_n, layers.count());
+  const int with_rows = PAS_CHANNEL_PITCH(s.nc) > 4 ? 1 : 0;   // the multiple-scattering rows kernel: > 4 channels
+  switch (s.nc) {
+#define PAS_CASE(N) \
+  case N: ray_setup_kernel<N><<<grid, 256, 0, stream>>>(g, T, static_cast<char*>(setup), layers.begin, layers.stride, with_rows); break;
+    PAS_CASE(3) PAS_CASE(4) PAS_CASE(8) PAS_CASE(15) PAS_CASE(16)
+#undef PAS_CASE
+    default: return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
 }
 
 }  // namespace pas

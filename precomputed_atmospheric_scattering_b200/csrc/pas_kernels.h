@@ -82,7 +82,16 @@ cudaError_t launch_density_setup(const PasGeometry& g, const PasSpectrum& s, con
 // S.rgb (+)= L.dR, S.a (+)= (L.dM).r, M (+)= L.dM (model.cc:142-157).
 cudaError_t launch_single_scattering(const PasGeometry& g, const PasSpectrum& s, const float* T,
                                      float* dR, float* dM, FinalTables fin, LayerSet layers,
-                                     cudaStream_t stream);
+                                     cudaStream_t stream, const void* ray_setup = nullptr);
+
+// Per-ray setup tables shared by the single-scattering pass and every multiple-scattering pass of an
+// Init (sample records, path transmittances, texel permutation: what their blocks would otherwise
+// compute in a latency-bound prologue, once per pass). ray_setup_bytes: size of the table, 0 when the
+// table sizes do not take the kernels that use it; the passes then compute their prologues themselves
+// (as they do when given ray_setup = nullptr).
+size_t ray_setup_bytes(const PasGeometry& g, int nc);
+cudaError_t launch_ray_setup(const PasGeometry& g, const PasSpectrum& s, const float* T, void* ray_setup,
+                             LayerSet layers, cudaStream_t stream);
 
 // Scattering density of `order` >= 2 (functions.glsl:1348-1367) for layers [k_begin, k_end).
 // Reads dR, dM (order 2) or dS (order >= 3) and row 0 of dE. Every texel is also stored to the
@@ -107,7 +116,7 @@ cudaError_t launch_indirect_irradiance(const PasGeometry& g, const PasSpectrum& 
 // S.rgb += L.dS / RayleighPhaseFunction(nu) (model.cc:192-208).
 cudaError_t launch_multiple_scattering(const PasGeometry& g, const PasSpectrum& s, const float* T,
                                        const float* dJ, float* dS, FinalTables fin, LayerSet layers,
-                                       cudaStream_t stream);
+                                       cudaStream_t stream, const void* ray_setup = nullptr);
 
 // ---- multi-GPU exchange over peer memory (peer_exchange.cu) ---------------------------------------
 // Flag array of a rank: PAS_FLAG_CHANNELS independent barrier sequences ("channels": main stream, side

@@ -334,6 +334,7 @@ struct pas_model {
   void* host_out[4] = {nullptr, nullptr, nullptr, nullptr};  // indexed by pas_texture
   bool host_own_layers = false;     // multi-GPU: copy out only the layers this rank computed (shared host buffers)
   DeviceBuffer T, dE, dR, dM, dJ, dS, dirs, G, cR, cM, T_rgb, scratch;
+  DeviceBuffer ray_setup;           // per-ray tables of the ray-march passes (pas::launch_ray_setup), or empty
   DeviceBuffer S, M, E, T_rgba;
   DeviceBuffer render_in[4], render_out[2];  // staging of host-pointer render queries
   float last_render_ms = 0.f;
@@ -631,6 +632,7 @@ pas_status allocate(pas_model* m) {
   PAS_CUDA(m->G.ensure((size_t)z.r_n * PAS_DIR_THETA * PAS_MAX_CH * sizeof(float)));
   PAS_CUDA(m->cR.ensure((size_t)z.r_n * PAS_MAX_CH * sizeof(float)));
   PAS_CUDA(m->cM.ensure((size_t)z.r_n * PAS_MAX_CH * sizeof(float)));
+  if (pas::ray_setup_bytes(m->geom, max_nc) > 0) PAS_CUDA(m->ray_setup.ensure(pas::ray_setup_bytes(m->geom, max_nc)));
   PAS_CUDA(m->S.ensure(m->n_s() * m->s_texel_bytes()));
   if (!m->combined) PAS_CUDA(m->M.ensure(m->n_s() * m->s_texel_bytes()));
   PAS_CUDA(m->E.ensure(m->n_e() * 16));
@@ -727,13 +729,19 @@ pas_status run_phase(pas_model* m, int gi, int phase, int order, bool accumulate
       PAS_CUDA(pas::launch_density_setup(g, sp, m->T.f(), static_cast<PasDensityDir*>(m->dirs.p),
                                          m->G.f(), m->cR.f(), m->cM.f(), stream));
       m->launches += 2;
+      if (m->ray_setup.p != nullptr) {
+        // sample records / path transmittances / permutations of this rank's rays, once for the single-
+        // scattering pass and all the multiple-scattering passes of this channel group
+        PAS_CUDA(pas::launch_ray_setup(g, sp, m->T.f(), m->ray_setup.p, ks, stream));
+        m->launches += 1;
+      }
       break;
     case 1:
       PAS_CUDA(pas::launch_direct_irradiance(g, sp, m->T.f(), m->dE.f(), fin, stream));
       m->launches += 1;
       break;
     case 2:
-      PAS_CUDA(pas::launch_single_scattering(g, sp, m->T.f(), m->dR.f(), m->dM.f(), fin, ks, stream));
+      PAS_CUDA(pas::launch_single_scattering(g, sp, m->T.f(), m->dR.f(), m->dM.f(), fin, ks, stream, m->ray_setup.p));
       m->launches += 1;
       break;
     case 3:
@@ -817,7 +825,7 @@ pas_status run_phase(pas_model* m, int gi, int phase, int order, bool accumulate
       break;
     }
     case 5:
-      PAS_CUDA(pas::launch_multiple_scattering(g, sp, m->T.f(), m->cur_dJ(), ds_out, fin, ks, stream));
+      PAS_CUDA(pas::launch_multiple_scattering(g, sp, m->T.f(), m->cur_dJ(), ds_out, fin, ks, stream, m->ray_setup.p));
       m->launches += 1;
       break;
     case 6:
@@ -1544,6 +1552,11 @@ pas_status pas_model_run_phase(pas_model* m, int phase, int order) {
   if (m == nullptr) return fail(PAS_ERR_INVALID_ARGUMENT, "model is NULL");
   if (m->groups.size() != 1) return fail(PAS_ERR_UNSUPPORTED, "single passes need <= 16 channels");
   PAS_CUDA(cudaSetDevice(m->device));
+  if ((phase == 2 || phase == 5) && m->ray_setup.p != nullptr) {
+    // single passes may follow a pas_model_write_intermediate("transmittance"): the ray tables are rebuilt
+    // from the transmittance buffer as it stands
+    PAS_CUDA(pas::launch_ray_setup(m->geom, m->groups[0], m->T.f(), m->ray_setup.p, m->layers(), m->stream));
+  }
   pas_status st = run_phase(m, 0, phase, order, false, m->stream, m->dS.f(), m->dS.f());
   if (st != PAS_OK) return st;
   PAS_CUDA(cudaStreamSynchronize(m->stream));

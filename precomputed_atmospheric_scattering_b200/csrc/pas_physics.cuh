@@ -78,7 +78,10 @@ PAS_HD double coord_from_unit(double x, int n) { return 0.5 / n + x * (1.0 - 1.0
 // Density profile (functions.glsl:263-273).
 PAS_HD double profile_density(const double (*P)[5], double h) {
   const double* L = h < P[0][0] ? P[0] : P[1];
-  return d_clamp(L[1] * exp(L[2] * h) + L[3] * h + L[4], 0.0, 1.0);
+  // (a layer without exponential term -- the ozone layers, the zero layers padded in front -- skips the
+  // fp64 exp: 0 * exp(x) is exactly 0 for every finite exp(x))
+  const double e = L[1] != 0.0 ? L[1] * exp(L[2] * h) : 0.0;
+  return d_clamp(e + L[3] * h + L[4], 0.0, 1.0);
 }
 
 // Distances to the boundaries and the ground test (functions.glsl:207-246), as written.
