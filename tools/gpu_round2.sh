@@ -30,7 +30,7 @@ fi
 if [ -n "$NCU" ]; then
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/${TAG}_ncu_bench.log 2>&1
 tail -2 gpurun_out/${TAG}_ncu_bench.log | cut -c1-300
-ncu --set full --clock-control none --import-source on -k regex:'density_kernel|multiple_scattering|single_scattering' -s 4 -c 7 -o gpurun_out/${TAG}_prof python tools/ncu_target.py > gpurun_out/${TAG}_ncu_full.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:'density_kernel|multiple_scattering|single_scattering|ray_setup' -s 5 -c 8 -o gpurun_out/${TAG}_prof python tools/ncu_target.py > gpurun_out/${TAG}_ncu_full.log 2>&1
 tail -2 gpurun_out/${TAG}_ncu_full.log
 fi
 ls -la gpurun_out | tail -12

@@ -24,6 +24,8 @@ def key_of(name):
         return "multiple_scattering"
     if "single_scattering" in name:
         return "single_scattering"
+    if "ray_setup" in name:
+        return "ray_setup"
     return None
 
 

@@ -5,7 +5,9 @@ flt = sys.argv[2]; top = int(sys.argv[3]) if len(sys.argv) > 3 else 14
 name, c = None, collections.Counter()
 def flush():
     if name and flt in name:
-        print(name[-70:], "total", sum(c.values()))
+        dem = subprocess.run(["c++filt", name], capture_output=True, text=True).stdout.strip()
+        dem = re.sub(r"pas::\(anonymous namespace\)::|void ", "", dem).split("(")[0]
+        print(dem[:110], "total", sum(c.values()))
         print("   " + " ".join(f"{k}={v}" for k, v in c.most_common(top)))
 for line in out.splitlines():
     m = re.search(r"Function : (\S+)", line)
