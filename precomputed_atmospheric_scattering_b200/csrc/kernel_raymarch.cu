@@ -278,6 +278,12 @@ multiple_scattering_kernel(const __grid_constant__ PasGeometry g,
   const Tap tnu = make_tap((nu_d + 1.0) * 0.5 * (nu_n - 1), nu_n);
   const int slab0 = tnu.i0 * mu_s_n, slab1 = tnu.i1 * mu_s_n;
   const float wnu = tnu.w;
+  // Texels whose nu lies exactly on a slab (every texel whose nu is not clamped, about 70 %) need 2
+  // instead of 4 texel reads per sample; consecutive texels share their slab and mostly their clamping,
+  // so whole warps qualify without sorting the row (the rows kernel below sorts it).
+  const bool on_slab = !active || wnu == 0.0f || wnu == 1.0f || tnu.i0 == tnu.i1;
+  const bool warp_on_slab = __all_sync(0xffffffffu, on_slab);
+  const int slab_s = wnu == 1.0f ? slab1 : slab0;
   MuSMap map;
   map.H2 = (float)(g.H * g.H);
   map.d_min = (float)(g.top - g.bottom);
@@ -330,17 +336,29 @@ multiple_scattering_kernel(const __grid_constant__ PasGeometry g,
         const float xs = f_clamp(f_mu_s_texel_x(map, bottom * mu_s_i), 0.0f, map.scale);
         const Tap tm = make_tap_f(xs, mu_s_n);
         const float wm = tm.w;
-        // the four corner weights of the (mu_s, nu) bilinear fetch
-        const float w11 = wnu * wm, w10 = wnu - w11, w01 = wm - w11, w00 = 1.0f - wnu - wm + w11;
-        const float4* a0 = buf + slab0 + tm.i0;
-        const float4* a1 = buf + slab0 + tm.i1;
-        const float4* b0 = buf + slab1 + tm.i0;
-        const float4* b1 = buf + slab1 + tm.i1;
         const float4* tw4 = reinterpret_cast<const float4*>(sTw[i]);
+        if (warp_on_slab) {
+          const float4* a0 = buf + slab_s + tm.i0;
+          const float4* a1 = buf + slab_s + tm.i1;
+          const float w0 = 1.0f - wm;
 #pragma unroll
-        for (int q = 0; q < Q; ++q) {
-          fma4(acc[q], combine4(w00, a0[q * pitch], w01, a1[q * pitch], w10, b0[q * pitch], w11, b1[q * pitch]),
-               tw4[q]);
+          for (int q = 0; q < Q; ++q) {
+            const float4 u = a0[q * pitch], v = a1[q * pitch];
+            fma4(acc[q], make_float4(fmaf(w0, u.x, wm * v.x), fmaf(w0, u.y, wm * v.y), fmaf(w0, u.z, wm * v.z),
+                                     fmaf(w0, u.w, wm * v.w)), tw4[q]);
+          }
+        } else {
+          // the four corner weights of the (mu_s, nu) bilinear fetch
+          const float w11 = wnu * wm, w10 = wnu - w11, w01 = wm - w11, w00 = 1.0f - wnu - wm + w11;
+          const float4* a0 = buf + slab0 + tm.i0;
+          const float4* a1 = buf + slab0 + tm.i1;
+          const float4* b0 = buf + slab1 + tm.i0;
+          const float4* b1 = buf + slab1 + tm.i1;
+#pragma unroll
+          for (int q = 0; q < Q; ++q) {
+            fma4(acc[q], combine4(w00, a0[q * pitch], w01, a1[q * pitch], w10, b0[q * pitch], w11, b1[q * pitch]),
+                 tw4[q]);
+          }
         }
       }
     }

@@ -163,17 +163,37 @@ void spectral_channels(unsigned num_precomputed_wavelengths, std::vector<double>
 struct BufferPool {
   std::mutex mu;
   std::multimap<std::pair<int, size_t>, void*> free_list;
+  size_t pooled = 0;           // bytes parked in the pool
+  // PAS_POOL_MAX_MB (default 16 GiB): what the pool may keep; a buffer that does not fit is freed at once
+  // (a process that walks through many table sizes would otherwise pin every size it has ever used)
+  size_t cap = [] {
+    const char* e = getenv("PAS_POOL_MAX_MB");
+    const long long mb = e != nullptr ? atoll(e) : 0;
+    return (size_t)(mb > 0 ? mb : 16384) << 20;
+  }();
   void* take(int device, size_t bytes) {
     std::lock_guard<std::mutex> lock(mu);
     auto it = free_list.find({device, bytes});
     if (it == free_list.end()) return nullptr;
     void* p = it->second;
     free_list.erase(it);
+    pooled -= bytes;
     return p;
   }
   void give(int device, size_t bytes, void* p) {
-    std::lock_guard<std::mutex> lock(mu);
-    free_list.insert({{device, bytes}, p});
+    {
+      std::lock_guard<std::mutex> lock(mu);
+      if (pooled + bytes <= cap) {
+        free_list.insert({{device, bytes}, p});
+        pooled += bytes;
+        return;
+      }
+    }
+    int current = 0;
+    cudaGetDevice(&current);
+    cudaSetDevice(device);
+    cudaFree(p);   // synchronises with the device: the buffer's last user has finished
+    cudaSetDevice(current);
   }
   void release_all() {
     std::lock_guard<std::mutex> lock(mu);
@@ -184,6 +204,7 @@ struct BufferPool {
       cudaFree(kv.second);
     }
     free_list.clear();
+    pooled = 0;
     cudaSetDevice(current);
   }
 };
