@@ -382,6 +382,9 @@ def run_b200(args, rank, world_size, local_rank):
     clocks = sampler.finish()
     ms_per_step = world.max_over_ranks(sum(device_ms) / len(device_ms))
     wall_ms = world.max_over_ranks(wall_ms)
+    if os.environ.get("PAS_BENCH_RANK_PHASES"):
+        # per-rank phase timings (which slab is the slow one): one JSON line per rank on stderr
+        print(json.dumps({"rank": rank, "phases_ms": {k: round(v, 4) for k, v in phases.items()}}), file=sys.stderr, flush=True)
 
     # ---- parity of the tables just timed, on every rank, outside the timed region ---------------------
     parity = None
