@@ -27,6 +27,7 @@ UNIQUE_ID_BYTES = 128  # PAS_NCCL_UNIQUE_ID_BYTES
 _PEER_WORLDS = set()   # (rank, world) for which this process has agreed on the peer exchange
 _ARENAS = {}           # (rank, world) -> Arena: the symmetric arena of this process in that world
 _NO_SYMM = set()       # (rank, world) for which the symmetric exchange was tried and is unavailable
+_RETIRED_ARENAS = []   # arenas replaced by larger ones; never unmapped while the process lives
 
 
 class Arena:
@@ -130,6 +131,9 @@ def attach(model, group=None, exchange: Optional[str] = None) -> Tuple[int, int]
                 except Exception as e:
                     error = e
                 if _all_ok(error is None, group):
+                    if (rank, world) in _ARENAS:
+                        # models attached earlier keep pointing into the smaller arena: it stays mapped
+                        _RETIRED_ARENAS.append(_ARENAS[(rank, world)])
                     _ARENAS[(rank, world)] = arena
                 else:
                     arena = None
