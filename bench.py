@@ -647,11 +647,18 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS))
+    ap.add_argument("--wavelengths", type=int, default=0,
+                    help="override the wavelength count of the config (scaling studies: --config 4 --wavelengths 3)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world_size = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.wavelengths and args.wavelengths != CONFIGS[args.config]["wavelengths"]:
+        c = CONFIGS[args.config]
+        c["workload"] = c["workload"].replace(f"{c['wavelengths']} precomputed wavelengths", f"{args.wavelengths} precomputed wavelengths")
+        c["metric"] = c["metric"].replace(f"{c['wavelengths']}_wavelengths", f"{args.wavelengths}_wavelengths")
+        c["wavelengths"] = args.wavelengths
     if args.impl == "reference":
         run_reference(args, rank)
         return

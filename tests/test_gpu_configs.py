@@ -150,6 +150,24 @@ def test_config5_batch_matches_oracle_and_blocking_init(pas, orc):
         m.close()
 
 
+@pytest.mark.parametrize("n", [15, 8])
+def test_wide_rows_with_many_channels_match_the_oracle(pas, orc, n):
+    """Rows of 1024 texels (8 nu x 128 mu_s, the row of config 4) with 8 / 15 / 16 channels per launch: the
+    generic one-block-per-row ray marches with their per-warp on-slab path (config 4 itself is checked at 3
+    channels above). Chained against the oracle on a small table with that row, every texel."""
+    sizes = dict(transmittance_width=64, transmittance_height=16, scattering_r=4, scattering_mu=8,
+                 scattering_mu_s=128, scattering_nu=8, irradiance_width=16, irradiance_height=4)
+    spec = pas.small_planet()
+    spec.num_precomputed_wavelengths = n if n == 15 else 24      # 24 -> groups of 16 + 8 channels
+    model = pas.Model.from_spec(spec, sizes=sizes)
+    model.set_capture(True)
+    model.Init(3)
+    want = oracle_for(pas, orc, spec, model, oracle_sizes(sizes)).precompute(3)
+    for key in ("delta_density_2", "delta_multiple_2", "delta_density_3", "delta_multiple_3"):
+        assert_close(key, model.intermediate(key), want[key])
+    model.close()
+
+
 @pytest.mark.timeout(900)
 def test_config5_full_size_batch_and_renders(pas, orc):
     """The full 64-atmosphere batch at the reference's table sizes, then 1080p renders of the
