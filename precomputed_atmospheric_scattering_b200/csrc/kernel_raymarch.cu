@@ -424,6 +424,22 @@ __device__ __forceinline__ void copy16(void* dst, const void* src, int n, int ti
 //    functions.glsl:923-925) need 2 instead of 4 texel reads per sample. The block's texels are
 //    permuted so that those come first and whole warps take the short path (bit-identical: the
 //    skipped terms are exact zeros).
+//  * staged rows split by texel parity: a lane reads the two neighbouring mu_s texels (i0, i0 + 1) of a
+//    slab with two 128-bit loads, and a quarter warp (the unit the shared-memory pipe serves per
+//    wavefront) holds 8 consecutive columns whose i0 spread over 8 s texels, s = the local stretch
+//    of the mu_s map between the texel and the sample (up to ~2). With the texels of a plane in
+//    their natural order two lanes hit the same 16-byte bank group as soon as s > 1 (1.23 extra
+//    wavefronts per load, measured and reproduced by a model of the pipe). Here plane positions
+//    [0, W/2) hold the even texels and [HALF, HALF + W/2) the odd ones; one load takes the even
+//    texel of every lane's pair, the other the odd one: 8 lanes then cover 8 s / 2 consecutive
+//    positions and stay conflict-free up to s = 2 (0.58 extra wavefronts per load left, from quarter
+//    warps that straddle two slabs).
+//    HALF = 4 (mod 8) and pitch = 4 / Q (mod 8) keep the staging stores of a quarter warp (8 / Q
+//    consecutive texels x Q planes) on 8 different bank groups.
+__host__ __device__ constexpr int rows_half(int width) { return width / 2 + 4; }
+template <int Q>
+__host__ __device__ constexpr int rows_pitch(int width) { return 2 * rows_half(width) + (Q > 1 ? 4 / Q : 0); }
+
 struct __align__(16) SlotSample {
   int row[4];       // row offset (in texels) held by each slot during this sample
   float w[4];       // weight of each slot
@@ -532,7 +548,7 @@ multiple_scattering_rows_kernel(const __grid_constant__ PasGeometry g,
   const int tid = threadIdx.x;
   const int j = blockIdx.x, k = k_begin + blockIdx.y * k_stride;
   const int mu_n = g.sz.mu_n, nu_n = g.sz.nu_n, mu_s_n = g.sz.mu_s_n;
-  constexpr int pitch = ((WIDTH + 7) & ~7) + 8 / Q;
+  constexpr int HALF = rows_half(WIDTH), pitch = rows_pitch<Q>(WIDTH);
   float4* sRow = reinterpret_cast<float4*>(smem_dyn);  // [2][Q * pitch]
   const float4* dJ4 = reinterpret_cast<const float4*>(dJ);
 
@@ -563,7 +579,10 @@ multiple_scattering_rows_kernel(const __grid_constant__ PasGeometry g,
   const float wnu = tnu.w;
   const bool on_slab = wnu == 0.0f || wnu == 1.0f || tnu.i0 == tnu.i1;
   const bool warp_on_slab = __all_sync(0xffffffffu, on_slab);
-  const int slab_s = wnu == 1.0f ? slab1 : slab0;
+  // plane positions of the slabs (mu_s_n is even: a slab starts on an even texel); a lane on a slab
+  // takes that slab alone with weight 1, the others take slab0 and slab1
+  const int pos_a = (on_slab ? (wnu == 1.0f ? slab1 : slab0) : slab0) >> 1, pos_b = slab1 >> 1;
+  const float w_a = on_slab ? 1.0f : 1.0f - wnu, w_b = wnu;
   MuSMap map;
   map.H2 = (float)(g.H * g.H);
   map.d_min = (float)(g.top - g.bottom);
@@ -580,7 +599,8 @@ multiple_scattering_rows_kernel(const __grid_constant__ PasGeometry g,
 #pragma unroll
     for (int it = 0; it < Q; ++it) R0[it] = R1[it] = R2[it] = R3[it] = make_float4(0.f, 0.f, 0.f, 0.f);
     // flat vector f = tid + it * WIDTH of a row: plane f % Q = tid % Q, texel f / Q = tid / Q + it * (WIDTH / Q)
-    float4* const dst0 = sRow + (tid % Q) * pitch + tid / Q;
+    // (WIDTH / Q is even: the texels of a thread share their parity)
+    float4* const dst0 = sRow + (tid % Q) * pitch + ((tid / Q) >> 1) + ((tid / Q) & 1) * HALF;
 #define PAS_LOAD_SLOTS(S)                                                                \
     {                                                                                    \
       if ((S).mask & 1) { const float4* p = dJ4 + (size_t)(S).row[0] * Q + tid;          \
@@ -604,7 +624,7 @@ multiple_scattering_rows_kernel(const __grid_constant__ PasGeometry g,
 #pragma unroll
         for (int it = 0; it < Q; ++it) {
           const float4 v = combine4(s.w[0], R0[it], s.w[1], R1[it], s.w[2], R2[it], s.w[3], R3[it]);
-          dst[it * (WIDTH / Q)] = make_float4(v.x * tw.x, v.y * tw.y, v.z * tw.z, v.w * tw.w);
+          dst[it * (WIDTH / Q / 2)] = make_float4(v.x * tw.x, v.y * tw.y, v.z * tw.z, v.w * tw.w);
         }
       }
       const float s_d = s.d, s_inv_r = s.inv_r;
@@ -616,31 +636,50 @@ multiple_scattering_rows_kernel(const __grid_constant__ PasGeometry g,
       // mu_s at the sample: (r mu_s + d nu) / r_i (functions.glsl:1314)
       const float mu_s_i = f_clamp(fmaf(s_d, nu, r_mu_s) * s_inv_r, -1.0f, 1.0f);
       const float xs = f_clamp(f_mu_s_texel_x(map, bottom * mu_s_i), 0.0f, map.scale);
-      const Tap tm = make_tap_f(xs, mu_s_n);
-      const float wm = tm.w;
+      const Tap tm = make_tap_f(xs, mu_s_n);   // i0 <= mu_s_n - 2, i1 = i0 + 1
+      // the even and the odd texel of the pair (i0, i0 + 1), with their weights
+      const bool odd0 = (tm.i0 & 1) != 0;
+      const float4* pe = buf + ((tm.i0 + 1) >> 1);
+      const float4* po = buf + HALF + (tm.i0 >> 1);
+      const float we = odd0 ? tm.w : 1.0f - tm.w, wo = odd0 ? 1.0f - tm.w : tm.w;
       if (warp_on_slab) {
-        const float4* a0 = buf + slab_s + tm.i0;
-        const float4* a1 = buf + slab_s + tm.i1;
-        const float w0 = 1.0f - wm;
+        const float4* ae = pe + pos_a;
+        const float4* ao = po + pos_a;
 #pragma unroll
         for (int q = 0; q < Q; ++q) {
-          const float4 u = a0[q * pitch], v = a1[q * pitch];
-          acc[q].x = fmaf(w0, u.x, fmaf(wm, v.x, acc[q].x));
-          acc[q].y = fmaf(w0, u.y, fmaf(wm, v.y, acc[q].y));
-          acc[q].z = fmaf(w0, u.z, fmaf(wm, v.z, acc[q].z));
-          acc[q].w = fmaf(w0, u.w, fmaf(wm, v.w, acc[q].w));
+          const float4 u = ae[q * pitch], v = ao[q * pitch];
+          acc[q].x = fmaf(we, u.x, fmaf(wo, v.x, acc[q].x));
+          acc[q].y = fmaf(we, u.y, fmaf(wo, v.y, acc[q].y));
+          acc[q].z = fmaf(we, u.z, fmaf(wo, v.z, acc[q].z));
+          acc[q].w = fmaf(we, u.w, fmaf(wo, v.w, acc[q].w));
         }
       } else {
-        // the four corner weights of the (mu_s, nu) bilinear fetch
-        const float w11 = wnu * wm, w10 = wnu - w11, w01 = wm - w11, w00 = 1.0f - wnu - wm + w11;
-        const float4* a0 = buf + slab0 + tm.i0;
-        const float4* a1 = buf + slab0 + tm.i1;
-        const float4* b0 = buf + slab1 + tm.i0;
-        const float4* b1 = buf + slab1 + tm.i1;
+        // lanes on a slab read it alone: a quarter warp of them costs no wavefront on the second slab
+        {
+          const float4* ae = pe + pos_a;
+          const float4* ao = po + pos_a;
+          const float wae = w_a * we, wao = w_a * wo;
 #pragma unroll
-        for (int q = 0; q < Q; ++q) {
-          const float4 t = combine4(w00, a0[q * pitch], w01, a1[q * pitch], w10, b0[q * pitch], w11, b1[q * pitch]);
-          acc[q].x += t.x; acc[q].y += t.y; acc[q].z += t.z; acc[q].w += t.w;
+          for (int q = 0; q < Q; ++q) {
+            const float4 u = ae[q * pitch], v = ao[q * pitch];
+            acc[q].x = fmaf(wae, u.x, fmaf(wao, v.x, acc[q].x));
+            acc[q].y = fmaf(wae, u.y, fmaf(wao, v.y, acc[q].y));
+            acc[q].z = fmaf(wae, u.z, fmaf(wao, v.z, acc[q].z));
+            acc[q].w = fmaf(wae, u.w, fmaf(wao, v.w, acc[q].w));
+          }
+        }
+        if (!on_slab) {
+          const float4* be = pe + pos_b;
+          const float4* bo = po + pos_b;
+          const float wbe = w_b * we, wbo = w_b * wo;
+#pragma unroll
+          for (int q = 0; q < Q; ++q) {
+            const float4 u = be[q * pitch], v = bo[q * pitch];
+            acc[q].x = fmaf(wbe, u.x, fmaf(wbo, v.x, acc[q].x));
+            acc[q].y = fmaf(wbe, u.y, fmaf(wbo, v.y, acc[q].y));
+            acc[q].z = fmaf(wbe, u.z, fmaf(wbo, v.z, acc[q].z));
+            acc[q].w = fmaf(wbe, u.w, fmaf(wbo, v.w, acc[q].w));
+          }
         }
       }
     }
@@ -923,8 +962,9 @@ cudaError_t launch_multiple_nc(const PasGeometry& g, const PasSpectrum& s, const
   cudaError_t e;
   if (width == 256 && Q > 1) {
     auto kern = multiple_scattering_rows_kernel<NC>;  // the reference's 8 x 32 row
-    if ((e = prepare(kern, dyn)) != cudaSuccess) return e;
-    kern<<<grid, 256, dyn, stream>>>(g, s, T, dJ, dS, fin, layers.begin, layers.stride, static_cast<const char*>(setup));
+    const size_t dyn_rows = (size_t)2 * Q * rows_pitch<Q>(256) * sizeof(float4);
+    if ((e = prepare(kern, dyn_rows)) != cudaSuccess) return e;
+    kern<<<grid, 256, dyn_rows, stream>>>(g, s, T, dJ, dS, fin, layers.begin, layers.stride, static_cast<const char*>(setup));
   } else if (width == 256) {
     auto kern = multiple_scattering_kernel<NC, 256, 3, 256>;
     if ((e = prepare(kern, dyn)) != cudaSuccess) return e;
