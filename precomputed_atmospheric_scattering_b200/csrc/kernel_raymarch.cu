@@ -429,16 +429,22 @@ __device__ __forceinline__ void copy16(void* dst, const void* src, int n, int ti
 //    wavefront) holds 8 consecutive columns whose i0 spread over 8 s texels, s = the local stretch
 //    of the mu_s map between the texel and the sample (up to ~2). With the texels of a plane in
 //    their natural order two lanes hit the same 16-byte bank group as soon as s > 1 (1.23 extra
-//    wavefronts per load, measured and reproduced by a model of the pipe). Here plane positions
-//    [0, W/2) hold the even texels and [HALF, HALF + W/2) the odd ones; one load takes the even
-//    texel of every lane's pair, the other the odd one: 8 lanes then cover 8 s / 2 consecutive
-//    positions and stay conflict-free up to s = 2 (0.58 extra wavefronts per load left, from quarter
-//    warps that straddle two slabs).
+//    wavefronts per load, measured, and reproduced by tools/probe/ms_bank_model.py). Here a plane
+//    holds the even texels of slab n at positions [n P, n P + mu_s_n / 2) and the odd ones HALF
+//    further; one load takes the even texel of every lane's pair, the other the odd one: 8 lanes
+//    then cover 8 s / 2 consecutive positions and stay conflict-free up to s = 2. The slab pitch
+//    P = mu_s_n / 2 + 1 (odd) separates the two ends of a quarter warp that straddles two slabs
+//    (model: 5.23 wavefronts per 128-bit load in the natural order, 4.31 with the parity split and
+//    the lane predicate below, 3.96 with the odd slab pitch; 4 = no conflict, no broadcast).
 //    HALF = 4 (mod 8) and pitch = 4 / Q (mod 8) keep the staging stores of a quarter warp (8 / Q
 //    consecutive texels x Q planes) on 8 different bank groups.
-__host__ __device__ constexpr int rows_half(int width) { return width / 2 + 4; }
+//    Row shape taken: the reference's 8 x 32 (rows_shape_ok), so that every offset is a constant.
+constexpr int kRowsHalf = 128 + 8 + 4;   // 256 / 2 texels + one pad per slab, = 4 (mod 8)
 template <int Q>
-__host__ __device__ constexpr int rows_pitch(int width) { return 2 * rows_half(width) + (Q > 1 ? 4 / Q : 0); }
+__host__ __device__ constexpr int rows_pitch() { return 2 * kRowsHalf + (Q > 1 ? 4 / Q : 0); }
+inline bool rows_shape_ok(const PasGeometry& g) {
+  return g.sz.nu_n == 8 && g.sz.mu_s_n == 32;
+}
 
 struct __align__(16) SlotSample {
   int row[4];       // row offset (in texels) held by each slot during this sample
@@ -547,8 +553,10 @@ multiple_scattering_rows_kernel(const __grid_constant__ PasGeometry g,
 
   const int tid = threadIdx.x;
   const int j = blockIdx.x, k = k_begin + blockIdx.y * k_stride;
-  const int mu_n = g.sz.mu_n, nu_n = g.sz.nu_n, mu_s_n = g.sz.mu_s_n;
-  constexpr int HALF = rows_half(WIDTH), pitch = rows_pitch<Q>(WIDTH);
+  const int mu_n = g.sz.mu_n;
+  constexpr int nu_n = 8, mu_s_n = 32;   // rows_shape_ok
+  constexpr int HALF = kRowsHalf, pitch = rows_pitch<Q>();
+  constexpr int slab_pitch = mu_s_n / 2 + 1;
   float4* sRow = reinterpret_cast<float4*>(smem_dyn);  // [2][Q * pitch]
   const float4* dJ4 = reinterpret_cast<const float4*>(dJ);
 
@@ -575,13 +583,12 @@ multiple_scattering_rows_kernel(const __grid_constant__ PasGeometry g,
   const float r_mu_s = (float)(ray.r * mu_s_d);
   const float bottom = (float)g.bottom;
   const Tap tnu = make_tap((nu_d + 1.0) * 0.5 * (nu_n - 1), nu_n);
-  const int slab0 = tnu.i0 * mu_s_n, slab1 = tnu.i1 * mu_s_n;
   const float wnu = tnu.w;
   const bool on_slab = wnu == 0.0f || wnu == 1.0f || tnu.i0 == tnu.i1;
   const bool warp_on_slab = __all_sync(0xffffffffu, on_slab);
-  // plane positions of the slabs (mu_s_n is even: a slab starts on an even texel); a lane on a slab
-  // takes that slab alone with weight 1, the others take slab0 and slab1
-  const int pos_a = (on_slab ? (wnu == 1.0f ? slab1 : slab0) : slab0) >> 1, pos_b = slab1 >> 1;
+  // plane positions of the slabs; a lane on a slab takes that slab alone with weight 1, the others
+  // take slab0 and slab1
+  const int pos_a = (on_slab && wnu == 1.0f ? tnu.i1 : tnu.i0) * slab_pitch, pos_b = tnu.i1 * slab_pitch;
   const float w_a = on_slab ? 1.0f : 1.0f - wnu, w_b = wnu;
   MuSMap map;
   map.H2 = (float)(g.H * g.H);
@@ -599,8 +606,11 @@ multiple_scattering_rows_kernel(const __grid_constant__ PasGeometry g,
 #pragma unroll
     for (int it = 0; it < Q; ++it) R0[it] = R1[it] = R2[it] = R3[it] = make_float4(0.f, 0.f, 0.f, 0.f);
     // flat vector f = tid + it * WIDTH of a row: plane f % Q = tid % Q, texel f / Q = tid / Q + it * (WIDTH / Q)
-    // (WIDTH / Q is even: the texels of a thread share their parity)
-    float4* const dst0 = sRow + (tid % Q) * pitch + ((tid / Q) >> 1) + ((tid / Q) & 1) * HALF;
+    // (WIDTH / Q is a multiple of mu_s_n: the texels of a thread share their column, WIDTH / Q / mu_s_n
+    // slabs apart)
+    const int col0 = (tid / Q) % mu_s_n;
+    float4* const dst0 = sRow + (tid % Q) * pitch + (tid / Q) / mu_s_n * slab_pitch + (col0 >> 1) + (col0 & 1) * HALF;
+    const int dst_step = WIDTH / Q / mu_s_n * slab_pitch;
 #define PAS_LOAD_SLOTS(S)                                                                \
     {                                                                                    \
       if ((S).mask & 1) { const float4* p = dJ4 + (size_t)(S).row[0] * Q + tid;          \
@@ -624,7 +634,7 @@ multiple_scattering_rows_kernel(const __grid_constant__ PasGeometry g,
 #pragma unroll
         for (int it = 0; it < Q; ++it) {
           const float4 v = combine4(s.w[0], R0[it], s.w[1], R1[it], s.w[2], R2[it], s.w[3], R3[it]);
-          dst[it * (WIDTH / Q / 2)] = make_float4(v.x * tw.x, v.y * tw.y, v.z * tw.z, v.w * tw.w);
+          dst[it * dst_step] = make_float4(v.x * tw.x, v.y * tw.y, v.z * tw.z, v.w * tw.w);
         }
       }
       const float s_d = s.d, s_inv_r = s.inv_r;
@@ -960,9 +970,9 @@ cudaError_t launch_multiple_nc(const PasGeometry& g, const PasSpectrum& s, const
   if (layers.count() == 0) return cudaSuccess;
   const dim3 grid(g.sz.mu_n, layers.count());
   cudaError_t e;
-  if (width == 256 && Q > 1) {
+  if (Q > 1 && rows_shape_ok(g)) {
     auto kern = multiple_scattering_rows_kernel<NC>;  // the reference's 8 x 32 row
-    const size_t dyn_rows = (size_t)2 * Q * rows_pitch<Q>(256) * sizeof(float4);
+    const size_t dyn_rows = (size_t)2 * Q * rows_pitch<Q>() * sizeof(float4);
     if ((e = prepare(kern, dyn_rows)) != cudaSuccess) return e;
     kern<<<grid, 256, dyn_rows, stream>>>(g, s, T, dJ, dS, fin, layers.begin, layers.stride, static_cast<const char*>(setup));
   } else if (width == 256) {
