@@ -777,7 +777,10 @@ single_scattering_kernel(const __grid_constant__ PasGeometry g,
   const int t_w = WIDTH > 0 ? WIDTH : g.sz.t_w;
   const int width = WIDTH > 0 ? WIDTH : nu_n * mu_s_n;
   const int nthreads = WIDTH > 0 ? WIDTH : (int)blockDim.x;
-  const int pitch = plane_pitch<Q>(t_w);
+  // NU_LANES: the staged row is split by texel parity like the rows of multiple scattering (see
+  // kRowsHalf): even texels at [0, WIDTH / 2), odd texels HALF further, one load per parity
+  constexpr int HALF = WIDTH / 2 + 4;
+  const int pitch = NU_LANES ? 2 * HALF + (Q > 1 ? 4 / Q : 0) : plane_pitch<Q>(t_w);
   float4* sRow = reinterpret_cast<float4*>(smem_dyn);  // [2][Q * pitch]
   const float4* T4 = reinterpret_cast<const float4*>(T);
 
@@ -799,7 +802,7 @@ single_scattering_kernel(const __grid_constant__ PasGeometry g,
   const float nu = (float)nu_d;
   const float r_mu_s = (float)(ray.r * mu_s_d);
   const float x_max = (float)(t_w - 1);
-  auto rot = [](int v) { return NU_LANES ? v : rot8(v); };
+  auto rot = [](int v) { return NU_LANES ? (v >> 1) + (v & 1) * HALF : rot8(v); };
 
   float4 accR[Q], accM[Q];
 #pragma unroll
@@ -859,14 +862,17 @@ single_scattering_kernel(const __grid_constant__ PasGeometry g,
         const float sm = f_sat(fmaf(mu_s_i - cur.cos_h, cur.inv_sun_w, 0.5f));
         const float vis = sm * sm * fmaf(-2.0f, sm, 3.0f);
         const float wr = vis * cur.dens_r, wm = vis * cur.dens_m;
-        const float4* t0 = buf + rot(tu.i0);
-        const float4* t1 = buf + rot(tu.i1);
+        // NU_LANES: t0 = the even texel of the pair (i0, i0 + 1), t1 = the odd one
+        const bool swap = NU_LANES && (tu.i0 & 1) != 0;
+        const float4* t0 = buf + rot(swap ? tu.i1 : tu.i0);
+        const float4* t1 = buf + rot(swap ? tu.i0 : tu.i1);
+        const float w_t = swap ? 1.0f - tu.w : tu.w;
         // (folding the path transmittance into the staged row, as multiple scattering does, was measured
         // 1 % slower here: the staging sits on the critical path in front of the barrier)
         const float4* tw4 = reinterpret_cast<const float4*>(sTw[i]);
 #pragma unroll
         for (int q = 0; q < Q; ++q) {
-          const float4 tv = lerp4(tu.w, t0[q * pitch], t1[q * pitch]);
+          const float4 tv = lerp4(w_t, t0[q * pitch], t1[q * pitch]);
           const float4 t = tw4[q];
           const float4 v = make_float4(tv.x * t.x, tv.y * t.y, tv.z * t.z, tv.w * t.w);
           fma4(accR[q], v, make_float4(wr, wr, wr, wr));
@@ -1005,8 +1011,9 @@ cudaError_t launch_single_nc(const PasGeometry& g, const PasSpectrum& s, const f
   cudaError_t e;
   if (width == 256 && g.sz.t_w == 256) {
     auto kern = single_scattering_kernel<NC, 256, 2, 256, true>;  // 128 registers: the row slots stay in registers
-    if ((e = prepare(kern, dyn)) != cudaSuccess) return e;
-    kern<<<grid, 256, dyn, stream>>>(g, s, T, dR, dM, fin, layers.begin, layers.stride, static_cast<const char*>(setup));
+    const size_t dyn_split = (size_t)2 * Q * (2 * (256 / 2 + 4) + (Q > 1 ? 4 / Q : 0)) * sizeof(float4);
+    if ((e = prepare(kern, dyn_split)) != cudaSuccess) return e;
+    kern<<<grid, 256, dyn_split, stream>>>(g, s, T, dR, dM, fin, layers.begin, layers.stride, static_cast<const char*>(setup));
   } else if (threads <= 256) {
     auto kern = single_scattering_kernel<NC, 256, 3, 0, false>;
     if ((e = prepare(kern, dyn)) != cudaSuccess) return e;
