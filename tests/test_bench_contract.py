@@ -69,7 +69,8 @@ def test_ncu_census_gives_executed_fractions_below_one():
                 ops.get("FADD", 0) + 2 * ops.get("FADD2", 0))
         assert flop == pytest.approx(e["fp32_flop_executed"], rel=1e-6)
         frac = e["fp32_flop_executed"] / (e["ms_under_ncu"] * 1e-3) / 74.5e12
-        assert 0.05 < frac < 1.0, (key, frac)
+        # (the ray setup pass is fp64 geometry, latency bound: a few fp32 operations only)
+        assert (0.0 if key == "ray_setup" else 0.05) < frac < 1.0, (key, frac)
         # the executed fraction cannot exceed what the FMA pipe was busy
         assert frac <= e["fma_pipe_cycles_active_pct"] / 100 + 0.02, (key, frac)
         wf = e["l1_wavefronts_per_sm"] / e["sm_cycles_elapsed"]
