@@ -412,7 +412,7 @@ __device__ __forceinline__ void copy16(void* dst, const void* src, int n, int ti
 }
 
 // ---- multiple scattering, reference row width (256 texels = block size) -------------------------
-// Same mapping as above, with two changes that cut the L1 data-pipe wavefronts (the bound of this
+// Same mapping as above, with three changes that cut the L1 data-pipe wavefronts (the bound of this
 // kernel):
 //  * row slots: consecutive samples of a ray share on average 2.5 of their 4 (layer, mu) corner rows.
 //    Every thread keeps its 16-byte vectors of four rows in registers ("slots"); a per-block plan
