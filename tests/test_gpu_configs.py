@@ -168,6 +168,26 @@ def test_wide_rows_with_many_channels_match_the_oracle(pas, orc, n):
     model.close()
 
 
+@pytest.mark.parametrize("nu,mu_s", [(8, 32), (4, 64), (16, 16)])
+def test_rows_of_256_texels_in_every_shape_match_the_oracle(pas, orc, nu, mu_s):
+    """Rows of 256 texels with 15 channels and a 256-wide transmittance table, every texel chained against
+    the oracle: 8 x 32 (the reference's shape) takes the ray setup pass and the register-slot kernels with
+    their parity-split staged rows; the other factorisations of 256 take the ray setup pass for single
+    scattering and the generic 256-thread multiple-scattering kernel with more than 4 channels."""
+    sizes = dict(transmittance_width=256, transmittance_height=16, scattering_r=4, scattering_mu=8,
+                 scattering_mu_s=mu_s, scattering_nu=nu, irradiance_width=16, irradiance_height=4)
+    spec = pas.small_planet()
+    spec.num_precomputed_wavelengths = 15
+    model = pas.Model.from_spec(spec, sizes=sizes)
+    model.set_capture(True)
+    model.Init(3)
+    want = oracle_for(pas, orc, spec, model, oracle_sizes(sizes)).precompute(3)
+    for key in ("delta_rayleigh", "delta_mie", "delta_density_2", "delta_multiple_2", "delta_density_3",
+                "delta_multiple_3"):
+        assert_close(key, model.intermediate(key), want[key])
+    model.close()
+
+
 @pytest.mark.timeout(900)
 def test_config5_full_size_batch_and_renders(pas, orc):
     """The full 64-atmosphere batch at the reference's table sizes, then 1080p renders of the
