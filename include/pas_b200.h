@@ -124,8 +124,10 @@ pas_status pas_model_wait(pas_model* model);
  * destinations (NULL = not wanted; native texel format and size of pas_model_texture_info, i.e. what
  * pas_model_read_texture(as_float32 = 0) returns; page-locked memory for the copies to overlap).
  * Every later Init copies each table out as soon as its last writer is done -- T after the first
- * pass, the scattering table in bands of layers behind the last multiple-scattering pass -- and the
- * buffers are valid when pas_model_init / pas_model_wait returns. Pass four NULLs to unregister. */
+ * pass -- and the last multiple-scattering pass writes the scattering table into a page-locked
+ * destination itself, row by row as it finishes them (a pageable destination is copied in bands of
+ * layers behind that pass). The buffers are valid when pas_model_init / pas_model_wait returns. Pass
+ * four NULLs to unregister. */
 pas_status pas_model_set_host_outputs(pas_model* model, void* transmittance, void* scattering,
                                       void* single_mie, void* irradiance);
 /* Multi-GPU worlds over peer / symmetric memory: with own_layers_only != 0 a rank copies out only the

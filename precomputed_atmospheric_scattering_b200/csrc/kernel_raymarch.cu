@@ -168,8 +168,9 @@ __device__ __forceinline__ void ray_sample_transmittance(const PasGeometry& g, c
   }
 }
 
-// RGBA store / accumulate into a final table (fp32 or fp16 texels).
-__device__ __forceinline__ void final_rgba(void* base, size_t texel, float4 v, int half, bool add) {
+// RGBA store / accumulate into a final table (fp32 or fp16 texels). Returns the value of the texel
+// after the accumulation, before the rounding of the store.
+__device__ __forceinline__ float4 final_rgba(void* base, size_t texel, float4 v, int half, bool add) {
   if (half) {
     __half2* p = reinterpret_cast<__half2*>(base) + 2 * texel;
     if (add) {
@@ -185,6 +186,19 @@ __device__ __forceinline__ void final_rgba(void* base, size_t texel, float4 v, i
       v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
     }
     *p = v;
+  }
+  return v;
+}
+// The same texel into a host-mapped copy of the table (FinalTables::host_scattering), same bits.
+__device__ __forceinline__ void host_rgba(void* base, size_t texel, float4 v, int half) {
+  if (half) {
+    __half2 lo = __floats2half2_rn(v.x, v.y), hi = __floats2half2_rn(v.z, v.w);
+    uint2 u;
+    u.x = *reinterpret_cast<unsigned*>(&lo);
+    u.y = *reinterpret_cast<unsigned*>(&hi);
+    reinterpret_cast<uint2*>(base)[texel] = u;
+  } else {
+    reinterpret_cast<float4*>(base)[texel] = v;
   }
 }
 
@@ -382,8 +396,11 @@ multiple_scattering_kernel(const __grid_constant__ PasGeometry g,
   }
   // scattering += L . dS / RayleighPhaseFunction(nu) (model.cc:204-207), alpha += 0
   const float inv_pr = (float)(1.0 / rayleigh_phase(nu_d));
-  final_rgba(fin.scattering, texel, make_float4(rgb[0] * inv_pr, rgb[1] * inv_pr, rgb[2] * inv_pr, 0.f),
-             fin.half_precision, true);
+  const float4 total = final_rgba(fin.scattering, texel,
+                                  make_float4(rgb[0] * inv_pr, rgb[1] * inv_pr, rgb[2] * inv_pr, 0.f),
+                                  fin.half_precision, true);
+  // consecutive threads own consecutive texels: the host copy is written in full 32-byte sectors
+  if (fin.host_scattering != nullptr) host_rgba(fin.host_scattering, texel, total, fin.half_precision);
 }
 
 // ---- per-ray setup tables ------------------------------------------------------------------------------
@@ -713,8 +730,27 @@ multiple_scattering_rows_kernel(const __grid_constant__ PasGeometry g,
   }
   // scattering += L . dS / RayleighPhaseFunction(nu) (model.cc:204-207), alpha += 0
   const float inv_pr = (float)(1.0 / rayleigh_phase(nu_d));
-  final_rgba(fin.scattering, texel, make_float4(rgb[0] * inv_pr, rgb[1] * inv_pr, rgb[2] * inv_pr, 0.f),
-             fin.half_precision, true);
+  const float4 total = final_rgba(fin.scattering, texel,
+                                  make_float4(rgb[0] * inv_pr, rgb[1] * inv_pr, rgb[2] * inv_pr, 0.f),
+                                  fin.half_precision, true);
+  if (fin.host_scattering != nullptr) {
+    // Host copy of the row: the threads own the texels in permuted order, so the row goes through
+    // shared memory and leaves as 16-byte vectors in texel order (full PCIe write payloads).
+    __syncthreads();  // the staged rows are dead
+    const size_t row = ((size_t)k * mu_n + j) * WIDTH;
+    if (fin.half_precision) {
+      host_rgba(smem_dyn, (size_t)x, total, 1);
+      __syncthreads();
+      if (tid < WIDTH / 2) {
+        reinterpret_cast<uint4*>(reinterpret_cast<uint2*>(fin.host_scattering) + row)[tid] =
+            reinterpret_cast<const uint4*>(smem_dyn)[tid];
+      }
+    } else {
+      host_rgba(smem_dyn, (size_t)x, total, 0);
+      __syncthreads();
+      (reinterpret_cast<float4*>(fin.host_scattering) + row)[tid] = reinterpret_cast<const float4*>(smem_dyn)[tid];
+    }
+  }
 }
 
 // ---- single scattering ------------------------------------------------------------------------

@@ -21,6 +21,9 @@ struct FinalTables {
   float* irradiance;       // RGBA interleaved fp32 [j][i][4]
   int half_precision;      // scattering / single_mie stored as __half
   int accumulate;          // 0: first channel group overwrites, 1: adds (GL blend, model.cc:1083)
+  void* host_scattering;   // device-visible address of a pinned HOST copy of `scattering`, or nullptr: the
+                           // multiple-scattering pass that makes the table final stores every texel there
+                           // too, so that the read-back rides on the kernel instead of following it
 };
 
 // Multi-GPU: the same table in the memory of the other GPUs of the box (CUDA IPC mappings, NVLink).

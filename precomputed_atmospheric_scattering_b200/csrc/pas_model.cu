@@ -353,6 +353,8 @@ struct pas_model {
   cudaStream_t copy = nullptr;
   cudaEvent_t ev_copy = nullptr;
   void* host_out[4] = {nullptr, nullptr, nullptr, nullptr};  // indexed by pas_texture
+  void* host_S_dev = nullptr;       // device-visible address of host_out[SCATTERING] when that is pinned memory
+  void* host_S_now = nullptr;       // = host_S_dev while the pass that makes S final is being enqueued
   bool host_own_layers = false;     // multi-GPU: copy out only the layers this rank computed (shared host buffers)
   DeviceBuffer T, dE, dR, dM, dJ, dS, dirs, G, cR, cM, T_rgb, scratch;
   DeviceBuffer ray_setup;           // per-ray tables of the ray-march passes (pas::launch_ray_setup), or empty
@@ -634,6 +636,7 @@ pas::FinalTables final_tables(pas_model* m, bool accumulate) {
   f.irradiance = m->E.f();
   f.half_precision = m->half ? 1 : 0;
   f.accumulate = accumulate ? 1 : 0;
+  f.host_scattering = m->host_S_now;
   return f;
 }
 
@@ -1064,6 +1067,18 @@ pas_status pas_model_set_host_outputs(pas_model* m, void* transmittance, void* s
   m->host_out[PAS_TEXTURE_SCATTERING] = scattering;
   m->host_out[PAS_TEXTURE_SINGLE_MIE] = single_mie;
   m->host_out[PAS_TEXTURE_IRRADIANCE] = irradiance;
+  // Pinned (cudaHostAlloc / cudaHostRegister) destinations are visible to the device: the last
+  // multiple-scattering pass then writes the scattering table there itself. Pageable destinations are
+  // filled by copies behind the pass.
+  m->host_S_dev = nullptr;
+  static const bool no_fused = getenv("PAS_NO_FUSED_READBACK") != nullptr;
+  if (scattering != nullptr && !no_fused) {
+    cudaPointerAttributes attr{};
+    if (cudaPointerGetAttributes(&attr, scattering) == cudaSuccess && attr.type == cudaMemoryTypeHost) {
+      m->host_S_dev = attr.devicePointer;
+    }
+    cudaGetLastError();
+  }
   return PAS_OK;
 }
 
@@ -1140,8 +1155,10 @@ pas_status pas_model_init_async(pas_model* m, unsigned int num_scattering_orders
   };
   // Pipelined read-back (pas_model_set_host_outputs; one GPU, no captures): a table is copied to the
   // host as soon as its last writer is done -- T after the first pass, the single-Mie table after
-  // single scattering, E after the last irradiance pass, S in four bands of layers behind the four
-  // launches the last multiple-scattering pass is split into.
+  // single scattering, E after the last irradiance pass. S is written to the host by the last
+  // multiple-scattering pass itself when the destination is pinned memory (FinalTables::host_scattering);
+  // a pageable destination is filled in four bands of layers behind the four launches that pass is
+  // then split into.
   // Peer worlds with pas_model_set_host_output_mode(own layers only): every rank copies the layers of
   // the 3-D tables IT computed (rank 0 also T and E) into host buffers the ranks share, and the last
   // barrier of Init comes after those copies: when Init returns on any rank, the whole table is there.
@@ -1248,13 +1265,23 @@ pas_status pas_model_init_async(pas_model* m, unsigned int num_scattering_orders
       // (multi-GPU: the density table is complete once the exchange of phase 3 / 4 is done)
       if ((st = capture_copy(m, "delta_density_" + tag, m->cur_dJ(), m->n_s(), nc, off, true)) != PAS_OK) return st;
       if (pipe_out && last_group && order == num_scattering_orders) {
-        // E is final (side stream); S becomes final band by band
+        // E is final (side stream)
         if (lead) PAS_CUDA(copy_after(side, PAS_TEXTURE_IRRADIANCE, 0, m->n_e() * 16));
-        const int n_own = own.count(), parts = n_own >= 8 ? 4 : (n_own >= 2 ? 2 : 1);
-        for (int part = 0; part < parts; ++part) {
-          const pas::LayerSet band = sub_set(own, part * n_own / parts, (part + 1) * n_own / parts);
-          if ((st = run_phase(m, (int)gi, 5, (int)order, blend, main, ds_in, ds_out, 0, &band)) != PAS_OK) return st;
-          PAS_CUDA(copy_layers_after(main, PAS_TEXTURE_SCATTERING, band));
+        if (m->host_out[PAS_TEXTURE_SCATTERING] != nullptr && m->host_S_dev != nullptr) {
+          // S becomes final in this pass, and its host destination is pinned memory: the kernel writes
+          // every row it finishes to the host table as well -- no copy behind the pass
+          m->host_S_now = m->host_S_dev;
+          st = run_phase(m, (int)gi, 5, (int)order, blend, main, ds_in, ds_out);
+          m->host_S_now = nullptr;
+          if (st != PAS_OK) return st;
+        } else {
+          // pageable destination: S becomes final band by band, each band copied behind its launch
+          const int n_own = own.count(), parts = n_own >= 8 ? 4 : (n_own >= 2 ? 2 : 1);
+          for (int part = 0; part < parts; ++part) {
+            const pas::LayerSet band = sub_set(own, part * n_own / parts, (part + 1) * n_own / parts);
+            if ((st = run_phase(m, (int)gi, 5, (int)order, blend, main, ds_in, ds_out, 0, &band)) != PAS_OK) return st;
+            PAS_CUDA(copy_layers_after(main, PAS_TEXTURE_SCATTERING, band));
+          }
         }
       } else if ((st = run_phase(m, (int)gi, 5, (int)order, blend, main, ds_in, ds_out)) != PAS_OK) {
         return st;

@@ -493,9 +493,10 @@ def test_overlapped_schedule_is_bit_identical(pas, which, orders):
 @pytest.mark.parametrize("n,combined,half,orders", [(15, True, True, 4), (3, False, False, 3), (3, True, True, 1),
                                                    (24, True, False, 2)])
 def test_registered_host_outputs_equal_blocking_reads(pas, n, combined, half, orders):
-    """pas_model_set_host_outputs: Init copies T / S / single Mie / E into registered host buffers
-    while it runs (S in bands behind the split last multiple-scattering pass). Same bytes as reading
-    the tables after a plain Init -- also with captures on (plain copies at the end) and on re-Init."""
+    """pas_model_set_host_outputs: Init fills registered host buffers with T / S / single Mie / E while
+    it runs (S: written by the last multiple-scattering pass itself into a pinned destination, copied
+    in bands behind the split pass into a pageable one). Same bytes as reading the tables after a plain
+    Init -- also with captures on (plain copies at the end) and on re-Init."""
     import torch
     spec = pas.earth(n, half_precision=half, combine_scattering_textures=combined, max_sun_zenith_deg=102.0)
     ref = pas.Model.from_spec(spec)
@@ -504,11 +505,12 @@ def test_registered_host_outputs_equal_blocking_reads(pas, n, combined, half, or
     if not combined:
         which.append(pas.TEXTURE_SINGLE_MIE)
     want = {w: ref.texture(w, as_float32=False) for w in which}
-    for capture in (False, True):
+    for capture, pinned in ((False, True), (True, True), (False, False)):
         m = pas.Model.from_spec(spec)
         m.set_capture(capture)
-        bufs = {w: torch.zeros(want[w].shape, dtype=torch.float16 if want[w].dtype == np.float16 else torch.float32
-                               ).pin_memory().numpy() for w in which}
+        bufs = {w: torch.zeros(want[w].shape, dtype=torch.float16 if want[w].dtype == np.float16 else torch.float32)
+                for w in which}
+        bufs = {w: (t.pin_memory() if pinned else t).numpy() for w, t in bufs.items()}
         m.set_host_outputs(transmittance=bufs[pas.TEXTURE_TRANSMITTANCE], scattering=bufs[pas.TEXTURE_SCATTERING],
                            irradiance=bufs[pas.TEXTURE_IRRADIANCE],
                            single_mie_scattering=bufs.get(pas.TEXTURE_SINGLE_MIE))
@@ -517,6 +519,6 @@ def test_registered_host_outputs_equal_blocking_reads(pas, n, combined, half, or
                 b[...] = 0
             m.Init(orders)
             for w in which:
-                assert np.array_equal(bufs[w], want[w]), (w, capture)
+                assert np.array_equal(bufs[w], want[w]), (w, capture, pinned)
         m.close()
     ref.close()
