@@ -533,7 +533,7 @@ def run_b200(args, rank, world_size, local_rank):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": config_dict(args.config, world_size),
         "e2e": {"value": round(e2e_ms, 4), "unit": "ms", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "what": "Model(host arrays) + Init with T, S, E copied into registered pinned host buffers as they become final + destroy"
+                "what": "Model(host arrays) + Init with T, E copied into registered pinned host buffers as they become final and S written there by the last multiple-scattering pass itself + destroy"
                         + ("; one set of host tables shared by the ranks, every rank copies the layers it computed" if own_layers else "")},
         "gpu_launches": launches, "clocks": clocks, "parity": parity, "roofline": roofline,
         "phases_ms": {k: round(v, 4) for k, v in phases.items()},
