@@ -168,6 +168,31 @@ __device__ __forceinline__ void ray_sample_transmittance(const PasGeometry& g, c
   }
 }
 
+// Four 128-bit row loads (p, p + stride, ...) into a register slot, behind a block-uniform BRANCH on
+// `bit`. Written as `if (bit) { loads }`, ptxas emits predicated loads, and a predicated-off LDG still
+// takes an issue slot and one pass through the L1 data pipe (measured: the "misc" shared wavefronts of
+// the ray-march kernels are their predicated-off row loads, 10 % of the pipe that bounds them).
+// bra.uni keeps the branch; the destinations are read-write operands, so the loads land in the
+// slot's own registers and nothing waits for them here.
+template <int STRIDE_BYTES>
+__device__ __forceinline__ void load_slot4(float4 (&R)[4], const float4* p, int bit) {
+  asm volatile(
+      "{\n"
+      " .reg .pred take;\n"
+      " setp.ne.b32 take, %16, 0;\n"
+      " @!take bra.uni SKIP;\n"
+      " bar.warp.sync 0xffffffff;\n"
+      " ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%17];\n"
+      " ld.global.nc.v4.f32 {%4, %5, %6, %7}, [%17 + %18];\n"
+      " ld.global.nc.v4.f32 {%8, %9, %10, %11}, [%17 + %19];\n"
+      " ld.global.nc.v4.f32 {%12, %13, %14, %15}, [%17 + %20];\n"
+      "SKIP:\n"
+      "}\n"
+      : "+f"(R[0].x), "+f"(R[0].y), "+f"(R[0].z), "+f"(R[0].w), "+f"(R[1].x), "+f"(R[1].y), "+f"(R[1].z), "+f"(R[1].w),
+        "+f"(R[2].x), "+f"(R[2].y), "+f"(R[2].z), "+f"(R[2].w), "+f"(R[3].x), "+f"(R[3].y), "+f"(R[3].z), "+f"(R[3].w)
+      : "r"(bit), "l"(p), "n"(STRIDE_BYTES), "n"(2 * STRIDE_BYTES), "n"(3 * STRIDE_BYTES));
+}
+
 // RGBA store / accumulate into a final table (fp32 or fp16 texels). Returns the value of the texel
 // after the accumulation, before the rounding of the store.
 __device__ __forceinline__ float4 final_rgba(void* base, size_t texel, float4 v, int half, bool add) {
@@ -628,16 +653,19 @@ multiple_scattering_rows_kernel(const __grid_constant__ PasGeometry g,
     const int col0 = (tid / Q) % mu_s_n;
     float4* const dst0 = sRow + (tid % Q) * pitch + (tid / Q) / mu_s_n * slab_pitch + (col0 >> 1) + (col0 & 1) * HALF;
     const int dst_step = WIDTH / Q / mu_s_n * slab_pitch;
+#define PAS_LOAD_SLOT(R, S, T)                                                           \
+      if (Q == 4) {                                                                      \
+        load_slot4<WIDTH * 16>(reinterpret_cast<float4(&)[4]>(R), dJ4 + (size_t)(S).row[T] * Q + tid, (S).mask & (1 << T)); \
+      } else if ((S).mask & (1 << T)) {                                                  \
+        const float4* p = dJ4 + (size_t)(S).row[T] * Q + tid;                            \
+        _Pragma("unroll") for (int it = 0; it < Q; ++it) R[it] = __ldg(p + it * WIDTH);  \
+      }
 #define PAS_LOAD_SLOTS(S)                                                                \
     {                                                                                    \
-      if ((S).mask & 1) { const float4* p = dJ4 + (size_t)(S).row[0] * Q + tid;          \
-        _Pragma("unroll") for (int it = 0; it < Q; ++it) R0[it] = __ldg(p + it * WIDTH); } \
-      if ((S).mask & 2) { const float4* p = dJ4 + (size_t)(S).row[1] * Q + tid;          \
-        _Pragma("unroll") for (int it = 0; it < Q; ++it) R1[it] = __ldg(p + it * WIDTH); } \
-      if ((S).mask & 4) { const float4* p = dJ4 + (size_t)(S).row[2] * Q + tid;          \
-        _Pragma("unroll") for (int it = 0; it < Q; ++it) R2[it] = __ldg(p + it * WIDTH); } \
-      if ((S).mask & 8) { const float4* p = dJ4 + (size_t)(S).row[3] * Q + tid;          \
-        _Pragma("unroll") for (int it = 0; it < Q; ++it) R3[it] = __ldg(p + it * WIDTH); } \
+      PAS_LOAD_SLOT(R0, S, 0)                                                            \
+      PAS_LOAD_SLOT(R1, S, 1)                                                            \
+      PAS_LOAD_SLOT(R2, S, 2)                                                            \
+      PAS_LOAD_SLOT(R3, S, 3)                                                            \
     }
     SlotSample s = load_sample(&plan[0]);
     PAS_LOAD_SLOTS(s)
@@ -711,6 +739,7 @@ multiple_scattering_rows_kernel(const __grid_constant__ PasGeometry g,
       }
     }
 #undef PAS_LOAD_SLOTS
+#undef PAS_LOAD_SLOT
   }
   const size_t texel = ((size_t)k * mu_n + j) * WIDTH + x;
   float4* out = reinterpret_cast<float4*>(dS) + texel * Q;
