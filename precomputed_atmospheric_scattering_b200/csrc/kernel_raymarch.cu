@@ -882,10 +882,15 @@ single_scattering_kernel(const __grid_constant__ PasGeometry g,
 #define PAS_LOAD_T_SLOTS(S)                                                                          \
     {                                                                                                \
       const int y0_ = (S).y0 & 0xffff, y1_ = (S).y1, m_ = (S).y0 >> 16;                              \
-      if (m_ & 1) { const float4* p = T4 + (size_t)((y0_ & 1) == 0 ? y0_ : y1_) * WIDTH * Q + tid;   \
-        _Pragma("unroll") for (int it = 0; it < Q; ++it) A[it] = __ldg(p + it * WIDTH); }            \
-      if (m_ & 2) { const float4* p = T4 + (size_t)((y0_ & 1) == 1 ? y0_ : y1_) * WIDTH * Q + tid;   \
-        _Pragma("unroll") for (int it = 0; it < Q; ++it) B[it] = __ldg(p + it * WIDTH); }            \
+      const float4* pa_ = T4 + (size_t)((y0_ & 1) == 0 ? y0_ : y1_) * WIDTH * Q + tid;               \
+      const float4* pb_ = T4 + (size_t)((y0_ & 1) == 1 ? y0_ : y1_) * WIDTH * Q + tid;               \
+      if (Q == 4) {                                                                                  \
+        load_slot4<WIDTH * 16>(reinterpret_cast<float4(&)[4]>(A), pa_, m_ & 1);                      \
+        load_slot4<WIDTH * 16>(reinterpret_cast<float4(&)[4]>(B), pb_, m_ & 2);                      \
+      } else {                                                                                       \
+        if (m_ & 1) { _Pragma("unroll") for (int it = 0; it < Q; ++it) A[it] = __ldg(pa_ + it * WIDTH); } \
+        if (m_ & 2) { _Pragma("unroll") for (int it = 0; it < Q; ++it) B[it] = __ldg(pb_ + it * WIDTH); } \
+      }                                                                                              \
     }
     if (WIDTH > 0) PAS_LOAD_T_SLOTS(s)
     for (int i = 0; i < kSamples; ++i) {
