@@ -17,7 +17,7 @@ OBJ=precomputed_atmospheric_scattering_b200/csrc/build/kernel_raymarch.o
   echo "# TMA / bulk-copy opcodes (UBLKCP / UTMALDG / LDGSTS) in kernel_raymarch.o:"
   cuobjdump -sass $OBJ | grep -c "UBLKCP\|UTMALDG\|LDGSTS" || true; } > /tmp/so.txt
 cp /tmp/so.txt profiles/r2_sass_ops_raymarch.txt
-{ grep "^#" profiles/r2_ptxas.txt; python tools/ptxas_summary.py | grep -v "^#"; } > /tmp/ptx2.txt
+{ echo "# ptxas -v summary of the last build (tools/ptxas_summary.py): registers, spill stores/loads in bytes, static shared memory"; python tools/ptxas_summary.py | grep -v "^#"; } > /tmp/ptx2.txt
 cp /tmp/ptx2.txt profiles/r2_ptxas.txt
 python - <<PY
 import json
